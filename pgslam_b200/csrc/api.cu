@@ -1,0 +1,552 @@
+// api.cu — the extern "C" boundary declared in include/pgslam_b200.h.
+// Each function names, in the header, the pgslam call site it serves.
+#include <cstring>
+#include <mutex>
+
+#include "filters.cuh"
+#include "icp.cuh"
+#include "modules.h"
+
+using namespace pgs;
+
+struct pgs_ctx {
+  Ctx c;
+};
+struct pgs_cloud {
+  std::unique_ptr<Cloud> c;
+};
+struct pgs_filters {
+  Ctx* ctx;
+  std::vector<Module> mods;
+};
+struct pgs_matcher {
+  Ctx* ctx;
+  Module mod;
+  std::unique_ptr<Index> index;
+};
+struct pgs_outliers {
+  Ctx* ctx;
+  std::vector<Module> mods;
+};
+struct pgs_minimizer {
+  Ctx* ctx;
+  Module mod;
+};
+struct pgs_icp {
+  Ctx* ctx;
+  ChainConfig cfg;
+  std::unique_ptr<IcpEngine> engine;  // created on first fused use
+  pgs_filters reading_filters, reading_step_filters, reference_filters;
+  pgs_matcher matcher;
+  pgs_outliers outliers;
+  pgs_minimizer minimizer;
+};
+
+namespace {
+
+thread_local std::string g_no_ctx_error;
+
+pgs_status fail(Ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  else g_no_ctx_error = msg;
+  return (pgs_status)code;
+}
+
+#define PGS_API_BEGIN try {
+#define PGS_API_END(ctxptr)                                              \
+  }                                                                      \
+  catch (const pgs::Error& _ex) { return fail((ctxptr), _ex.code, _ex.what()); } \
+  catch (const std::exception& _ex) { return fail((ctxptr), PGS_CUDA_ERROR, _ex.what()); } \
+  return PGS_OK;
+
+Params kv_params(const char* const* kv, int nkv) {
+  Params p;
+  for (int i = 0; i < nkv; ++i) p[kv[2 * i]] = kv[2 * i + 1];
+  return p;
+}
+
+void copy_in(Ctx* ctx, void* dst, const void* src, size_t bytes, int on_device) {
+  if (!bytes) return;
+  PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  if (!on_device) ctx->sync();  // the caller may reuse its host buffer right after the call
+}
+void copy_out(Ctx* ctx, void* dst, const void* src, size_t bytes, int on_device) {
+  if (!bytes) return;
+  PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  if (!on_device) ctx->sync();
+}
+
+IcpEngine& engine_of(pgs_icp* icp) {
+  if (!icp->engine) icp->engine = std::make_unique<IcpEngine>(icp->ctx, icp->cfg);
+  return *icp->engine;
+}
+
+void wire_icp(pgs_icp* icp) {
+  Ctx* ctx = icp->ctx;
+  icp->reading_filters = pgs_filters{ctx, icp->cfg.reading_filters};
+  icp->reading_step_filters = pgs_filters{ctx, icp->cfg.reading_step_filters};
+  icp->reference_filters = pgs_filters{ctx, icp->cfg.reference_filters};
+  icp->matcher.ctx = ctx;
+  icp->matcher.mod = icp->cfg.matcher;
+  icp->outliers = pgs_outliers{ctx, icp->cfg.outlier_filters};
+  icp->minimizer = pgs_minimizer{ctx, icp->cfg.minimizer};
+}
+
+void matcher_find(pgs_matcher* m, const Cloud& reading, int32_t* d_ids, float* d_d2) {
+  if (!m->index) throw Error(PGS_INVALID_FIELD, "KDTreeMatcher: init() must be called before findClosests()");
+  const int k = (int)m->mod.integer("knn");
+  KnnJob job{m->index->view(), reading.feat.p, nullptr, (int)reading.n, d_ids, d_d2};
+  knn_batched(m->ctx, {job}, k, (float)m->mod.real("maxDist"));
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* pgs_version(void) { return "pgslam_b200 0.1 (sm_100a)"; }
+
+pgs_status pgs_ctx_create(int device, void* stream, pgs_ctx** out) {
+  Ctx* cp = nullptr;
+  PGS_API_BEGIN
+  if (!out) throw Error(PGS_INVALID_ARGUMENT, "out is NULL");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(PGS_CUDA_ERROR, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                    " (libpgslam_b200 has no CPU fallback)");
+  if (device < 0 || device >= count) throw Error(PGS_INVALID_ARGUMENT, "device index out of range");
+  PGS_CUDA(cudaSetDevice(device));
+  auto h = std::make_unique<pgs_ctx>();
+  h->c.device = device;
+  if (stream) {
+    h->c.stream = static_cast<cudaStream_t>(stream);
+    h->c.own_stream = false;
+  } else {
+    PGS_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    h->c.own_stream = true;
+  }
+  cudaDeviceProp prop;
+  PGS_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->c.num_sms = prop.multiProcessorCount;
+  // keep freed blocks in the stream-ordered pool: a registration allocates and
+  // frees dozens of temporaries and must not hit the OS allocator each time
+  cudaMemPool_t pool;
+  PGS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  PGS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  *out = h.release();
+  PGS_API_END(cp)
+}
+
+void pgs_ctx_destroy(pgs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  if (ctx->c.pinned) cudaFreeHost(ctx->c.pinned);
+  if (ctx->c.h_progress) cudaFreeHost((void*)ctx->c.h_progress);
+  for (auto& e : ctx->c.loop_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+const char* pgs_last_error(const pgs_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_no_ctx_error.c_str(); }
+
+pgs_status pgs_ctx_synchronize(pgs_ctx* ctx) {
+  PGS_API_BEGIN
+  ctx->c.sync();
+  PGS_API_END(&ctx->c)
+}
+
+uint64_t pgs_ctx_launch_count(const pgs_ctx* ctx) { return ctx->c.launches; }
+
+pgs_status pgs_ctx_set_profiling(pgs_ctx* ctx, int enabled) {
+  ctx->c.profiling = enabled != 0;
+  return PGS_OK;
+}
+
+pgs_status pgs_ctx_last_stage_times(const pgs_ctx* ctx, pgs_stage_times* out) {
+  *out = ctx->c.times;
+  return PGS_OK;
+}
+
+// ---- DataPoints ---------------------------------------------------------------
+pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, int on_device, pgs_cloud** out) {
+  PGS_API_BEGIN
+  if (!out || n < 0 || (n > 0 && !features4xN)) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_create: bad arguments");
+  if (n > 0x7fffffff - 1024) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_create: too many points");
+  PGS_CUDA(cudaSetDevice(ctx->c.device));
+  auto h = std::make_unique<pgs_cloud>();
+  h->c = std::make_unique<Cloud>(&ctx->c);
+  h->c->n = n;
+  h->c->feat.reset(&ctx->c, (size_t)n);
+  copy_in(&ctx->c, h->c->feat.p, features4xN, (size_t)n * sizeof(float4), on_device);
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_cloud_set_descriptor(pgs_cloud* c, const char* label, int span, const float* data, int on_device) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  if (span <= 0 || !label) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_set_descriptor: bad arguments");
+  Desc& d = c->c->add(label, span);
+  copy_in(ctx, d.data.p, data, (size_t)c->c->n * span * sizeof(float), on_device);
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_remove_descriptor(pgs_cloud* c, const char* label) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  if (!c->c->find(label)) throw Error(PGS_INVALID_FIELD, std::string("Cannot find descriptor ") + label);
+  c->c->remove(label);
+  PGS_API_END(ctx)
+}
+
+int64_t pgs_cloud_num_points(const pgs_cloud* c) { return c->c->n; }
+int pgs_cloud_num_descriptors(const pgs_cloud* c) { return (int)c->c->descs.size(); }
+
+pgs_status pgs_cloud_descriptor_info(const pgs_cloud* c, int index, char* label, int cap, int* span) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  if (index < 0 || index >= (int)c->c->descs.size()) throw Error(PGS_INVALID_FIELD, "descriptor index out of range");
+  const Desc& d = c->c->descs[index];
+  if (label && cap > 0) {
+    std::strncpy(label, d.label.c_str(), cap - 1);
+    label[cap - 1] = '\0';
+  }
+  if (span) *span = d.span;
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_get_features(const pgs_cloud* c, float* out4xN, int on_device) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  copy_out(ctx, out4xN, c->c->feat.p, (size_t)c->c->n * sizeof(float4), on_device);
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_get_descriptor(const pgs_cloud* c, const char* label, float* out, int on_device) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  const Desc* d = c->c->find(label);
+  if (!d) throw Error(PGS_INVALID_FIELD, std::string("Cannot find descriptor ") + label);
+  copy_out(ctx, out, d->data.p, (size_t)c->c->n * d->span * sizeof(float), on_device);
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_copy(const pgs_cloud* c, pgs_cloud** out) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_cloud>();
+  h->c = c->c->clone();
+  *out = h.release();
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_concatenate(pgs_cloud* a, const pgs_cloud* b) {
+  Ctx* ctx = a->c->ctx;
+  PGS_API_BEGIN
+  concatenate_cloud(*a->c, *b->c);
+  PGS_API_END(ctx)
+}
+
+void pgs_cloud_destroy(pgs_cloud* c) { delete c; }
+
+// ---- Transformation -------------------------------------------------------------
+pgs_status pgs_rigid_transform(pgs_cloud* c, const double T[16]) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN
+  rigid_transform_cloud(*c->c, T);
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_assemble(pgs_ctx* ctx, int n, const pgs_cloud* const* clouds, const double* T, pgs_cloud** out) {
+  PGS_API_BEGIN
+  if (n < 1) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_assemble: need at least one cloud");
+  auto h = std::make_unique<pgs_cloud>();
+  h->c = clouds[0]->c->clone();
+  for (int i = 1; i < n; ++i) {
+    auto tmp = clouds[i]->c->clone();
+    rigid_transform_cloud(*tmp, T + 16 * i);
+    concatenate_cloud(*h->c, *tmp);
+  }
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+// ---- DataPointsFilters ------------------------------------------------------------
+pgs_status pgs_filters_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t len, pgs_filters** out) {
+  PGS_API_BEGIN
+  YamlNode root = parse_yaml(std::string(yaml, len));
+  auto h = std::make_unique<pgs_filters>();
+  h->ctx = &ctx->c;
+  h->mods = module_list_from_yaml(Kind::DataPointsFilter, root);
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_filters_create(pgs_ctx* ctx, pgs_filters** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_filters>();
+  h->ctx = &ctx->c;
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_filters_append(pgs_filters* f, const char* name, const char* const* kv, int nkv) {
+  PGS_API_BEGIN
+  f->mods.push_back(create_module(Kind::DataPointsFilter, name, kv_params(kv, nkv)));
+  PGS_API_END(f->ctx)
+}
+
+int pgs_filters_count(const pgs_filters* f) { return (int)f->mods.size(); }
+
+pgs_status pgs_filters_apply(pgs_filters* f, pgs_cloud* c) {
+  PGS_API_BEGIN
+  std::vector<Cloud*> cl{c->c.get()};
+  apply_filters(f->ctx, f->mods, cl);
+  PGS_API_END(f->ctx)
+}
+
+void pgs_filters_destroy(pgs_filters* f) { delete f; }
+
+// ---- Matcher -----------------------------------------------------------------------
+pgs_status pgs_matcher_create(pgs_ctx* ctx, const char* name, const char* const* kv, int nkv, pgs_matcher** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_matcher>();
+  h->ctx = &ctx->c;
+  h->mod = create_module(Kind::Matcher, name, kv_params(kv, nkv));
+  if (h->mod.integer("knn") > 32) throw Error(PGS_INVALID_PARAMETER, "KDTreeMatcher: knn > 32 is not supported");
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_matcher_init(pgs_matcher* m, const pgs_cloud* reference) {
+  PGS_API_BEGIN
+  std::vector<std::unique_ptr<Index>> idx;
+  build_indices(m->ctx, {reference->c->feat.p}, {(int)reference->c->n}, nullptr, idx);
+  m->index = std::move(idx[0]);
+  PGS_API_END(m->ctx)
+}
+
+int pgs_matcher_knn(const pgs_matcher* m) { return (int)m->mod.integer("knn"); }
+
+pgs_status pgs_matcher_find(pgs_matcher* m, const pgs_cloud* reading, int32_t* ids, float* dists2, int on_device) {
+  PGS_API_BEGIN
+  const int k = (int)m->mod.integer("knn");
+  const size_t cnt = (size_t)reading->c->n * k;
+  if (on_device) {
+    matcher_find(m, *reading->c, ids, dists2);
+  } else {
+    DBuf<int32_t> di(m->ctx, cnt);
+    DBuf<float> dd(m->ctx, cnt);
+    matcher_find(m, *reading->c, di.p, dd.p);
+    di.download(ids, cnt);
+    dd.download(dists2, cnt);
+    m->ctx->sync();
+  }
+  PGS_API_END(m->ctx)
+}
+
+void pgs_matcher_destroy(pgs_matcher* m) { delete m; }
+
+// ---- OutlierFilters ------------------------------------------------------------------
+pgs_status pgs_outliers_create(pgs_ctx* ctx, pgs_outliers** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_outliers>();
+  h->ctx = &ctx->c;
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_outliers_append(pgs_outliers* o, const char* name, const char* const* kv, int nkv) {
+  PGS_API_BEGIN
+  o->mods.push_back(create_module(Kind::OutlierFilter, name, kv_params(kv, nkv)));
+  PGS_API_END(o->ctx)
+}
+
+pgs_status pgs_outliers_compute(pgs_outliers* o, const pgs_cloud* reading, const pgs_cloud* reference,
+                                const int32_t* ids, const float* dists2, int k, float* weights, int on_device) {
+  PGS_API_BEGIN
+  (void)reference;
+  (void)ids;
+  const int64_t nk = reading->c->n * k;
+  if (on_device) {
+    outlier_weights_device(o->ctx, o->mods, dists2, nk, weights);
+  } else {
+    DBuf<float> dd(o->ctx, (size_t)nk), dw(o->ctx, (size_t)nk);
+    copy_in(o->ctx, dd.p, dists2, (size_t)nk * sizeof(float), 0);
+    outlier_weights_device(o->ctx, o->mods, dd.p, nk, dw.p);
+    copy_out(o->ctx, weights, dw.p, (size_t)nk * sizeof(float), 0);
+  }
+  PGS_API_END(o->ctx)
+}
+
+void pgs_outliers_destroy(pgs_outliers* o) { delete o; }
+
+// ---- ErrorMinimizer --------------------------------------------------------------------
+pgs_status pgs_minimizer_create(pgs_ctx* ctx, const char* name, const char* const* kv, int nkv, pgs_minimizer** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_minimizer>();
+  h->ctx = &ctx->c;
+  h->mod = create_module(Kind::ErrorMinimizer, name, kv_params(kv, nkv));
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_minimizer_compute(pgs_minimizer* e, const pgs_cloud* reading, const pgs_cloud* reference,
+                                 const int32_t* ids, const float* dists2, const float* weights, int k, int on_device,
+                                 pgs_min_result* out) {
+  PGS_API_BEGIN
+  const size_t nk = (size_t)reading->c->n * k;
+  if (on_device) {
+    minimize_device(e->ctx, e->mod, *reading->c, *reference->c, ids, dists2, weights, k, out);
+  } else {
+    DBuf<int32_t> di(e->ctx, nk);
+    DBuf<float> dd(e->ctx, nk), dw(e->ctx, nk);
+    copy_in(e->ctx, di.p, ids, nk * sizeof(int32_t), 0);
+    copy_in(e->ctx, dd.p, dists2, nk * sizeof(float), 0);
+    copy_in(e->ctx, dw.p, weights, nk * sizeof(float), 0);
+    minimize_device(e->ctx, e->mod, *reading->c, *reference->c, di.p, dd.p, dw.p, k, out);
+  }
+  PGS_API_END(e->ctx)
+}
+
+void pgs_minimizer_destroy(pgs_minimizer* e) { delete e; }
+
+// ---- ICP / ICPSequence ---------------------------------------------------------------------
+pgs_status pgs_icp_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t len, pgs_icp** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_icp>();
+  h->ctx = &ctx->c;
+  h->cfg = chain_from_yaml(std::string(yaml, len));
+  wire_icp(h.get());
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_icp_create_default(pgs_ctx* ctx, pgs_icp** out) {
+  PGS_API_BEGIN
+  auto h = std::make_unique<pgs_icp>();
+  h->ctx = &ctx->c;
+  h->cfg = chain_default();
+  wire_icp(h.get());
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+void pgs_icp_destroy(pgs_icp* icp) { delete icp; }
+
+pgs_filters* pgs_icp_reading_filters(pgs_icp* icp) { return &icp->reading_filters; }
+pgs_filters* pgs_icp_reading_step_filters(pgs_icp* icp) { return &icp->reading_step_filters; }
+pgs_filters* pgs_icp_reference_filters(pgs_icp* icp) { return &icp->reference_filters; }
+pgs_matcher* pgs_icp_matcher(pgs_icp* icp) { return &icp->matcher; }
+pgs_outliers* pgs_icp_outliers(pgs_icp* icp) { return &icp->outliers; }
+pgs_minimizer* pgs_icp_minimizer(pgs_icp* icp) { return &icp->minimizer; }
+
+pgs_status pgs_icp_run(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference, const double T_init[16],
+                       pgs_icp_result* out) {
+  PGS_API_BEGIN
+  std::vector<const Cloud*> rd{reading->c.get()}, rf{reference->c.get()};
+  engine_of(icp).run_batch(rd, rf, T_init, out);
+  if (out->status != PGS_OK) {
+    static const char* why[] = {"", "ICP failed to converge (no outlier to filter / no point to minimize / bound exceeded)",
+                                "RigidTransformation: Error, rotation matrix is not orthogonal.", "invalid parameter",
+                                "reference cloud has no 'normals' descriptor (point-to-plane)"};
+    return fail(icp->ctx, out->status, out->status < 5 ? why[out->status] : "ICP failed");
+  }
+  PGS_API_END(icp->ctx)
+}
+
+pgs_status pgs_icp_set_map(pgs_icp* icp, const pgs_cloud* map) {
+  PGS_API_BEGIN
+  engine_of(icp).set_map(*map->c);
+  PGS_API_END(icp->ctx)
+}
+
+int pgs_icp_has_map(const pgs_icp* icp) { return icp->engine && icp->engine->has_map(); }
+
+pgs_status pgs_icp_run_sequence(pgs_icp* icp, const pgs_cloud* reading, const double T_init[16], pgs_icp_result* out) {
+  PGS_API_BEGIN
+  engine_of(icp).run_sequence(*reading->c, T_init, out);
+  if (out->status != PGS_OK) return fail(icp->ctx, out->status, "ICPSequence failed for this reading");
+  PGS_API_END(icp->ctx)
+}
+
+pgs_status pgs_icp_run_batch(pgs_icp* icp, int n_pairs, const pgs_cloud* const* readings,
+                             const pgs_cloud* const* references, const double* T_inits, pgs_icp_result* results) {
+  PGS_API_BEGIN
+  if (n_pairs <= 0) return PGS_OK;
+  std::vector<const Cloud*> rd(n_pairs), rf(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) { rd[i] = readings[i]->c.get(); rf[i] = references[i]->c.get(); }
+  engine_of(icp).run_batch(rd, rf, T_inits, results);
+  bool any_ok = false;
+  int first_bad = PGS_OK;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (results[i].status == PGS_OK) any_ok = true;
+    else if (first_bad == PGS_OK) first_bad = results[i].status;
+  }
+  if (!any_ok) return fail(icp->ctx, first_bad, "every pair of the batch failed");
+  PGS_API_END(icp->ctx)
+}
+
+pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
+                                 const double T_world_robot[16], double* weighted_point_used_ratio) {
+  PGS_API_BEGIN
+  Ctx* ctx = icp->ctx;
+  // Localizer.hpp:309-347, module by module, without leaving the device
+  auto ref = reference->c->clone();
+  std::vector<Cloud*> rl{ref.get()};
+  apply_filters(ctx, icp->cfg.reference_filters, rl);
+  pgs_matcher m;
+  m.ctx = ctx;
+  m.mod = icp->cfg.matcher;
+  std::vector<std::unique_ptr<Index>> idx;
+  build_indices(ctx, {ref->feat.p}, {(int)ref->n}, nullptr, idx);
+  m.index = std::move(idx[0]);
+  auto rd = reading->c->clone();
+  std::vector<Cloud*> dl{rd.get()};
+  apply_filters(ctx, icp->cfg.reading_filters, dl);
+  rigid_transform_cloud(*rd, T_world_robot);
+  apply_filters(ctx, icp->cfg.reading_step_filters, dl);
+  const int k = (int)m.mod.integer("knn");
+  const size_t nk = (size_t)rd->n * k;
+  DBuf<int32_t> ids(ctx, nk);
+  DBuf<float> d2(ctx, nk), w(ctx, nk);
+  matcher_find(&m, *rd, ids.p, d2.p);
+  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p);
+  double kept = 0, wsum = 0;
+  weights_ratio_device(ctx, d2.p, w.p, (int64_t)nk, &kept, &wsum);
+  if (!(kept > 0)) throw Error(PGS_CONVERGENCE_ERROR, "no point to minimize");
+  *weighted_point_used_ratio = wsum / (double)nk;
+  PGS_API_END(icp->ctx)
+}
+
+pgs_status pgs_icp_probe_residual(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
+                                  const double T[16], double* residual) {
+  PGS_API_BEGIN
+  Ctx* ctx = icp->ctx;
+  // LoopCloser.hpp:346-362: raw candidate cloud, un-centred, unfiltered
+  auto rd = reading->c->clone();
+  rigid_transform_cloud(*rd, T);
+  pgs_matcher m;
+  m.ctx = ctx;
+  m.mod = icp->cfg.matcher;
+  std::vector<std::unique_ptr<Index>> idx;
+  build_indices(ctx, {reference->c->feat.p}, {(int)reference->c->n}, nullptr, idx);
+  m.index = std::move(idx[0]);
+  const int k = (int)m.mod.integer("knn");
+  const size_t nk = (size_t)rd->n * k;
+  DBuf<int32_t> ids(ctx, nk);
+  DBuf<float> d2(ctx, nk), w(ctx, nk);
+  matcher_find(&m, *rd, ids.p, d2.p);
+  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p);
+  pgs_min_result mr;
+  minimize_device(ctx, icp->cfg.minimizer, *rd, *reference->c, ids.p, d2.p, w.p, k, &mr);
+  *residual = mr.residual;
+  PGS_API_END(icp->ctx)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

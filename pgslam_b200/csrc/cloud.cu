@@ -1,0 +1,119 @@
+// cloud.cu — context (stream, stream-ordered memory pool, pinned staging) and
+// the device-resident DataPoints container (types.h:20; LocalMap.hpp:85,214,222).
+#include <cstring>
+
+#include "core.cuh"
+
+namespace pgs {
+
+void* Ctx::alloc(size_t bytes) {
+  void* p = nullptr;
+  PGS_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+  return p;
+}
+
+void Ctx::free(void* p) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
+// Small host->device uploads (job tables, a few KB) go through a pinned ring so
+// that cudaMemcpyAsync never has to stage pageable memory behind a stream sync.
+void Ctx::upload_small(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  const size_t kRing = 4u << 20;
+  if (!pinned) {
+    PGS_CUDA(cudaHostAlloc(&pinned, kRing, cudaHostAllocDefault));
+    pinned_bytes = kRing;
+    pinned_head = 0;
+  }
+  if (bytes > pinned_bytes / 2) {
+    PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    PGS_CUDA(cudaStreamSynchronize(stream));
+    return;
+  }
+  size_t aligned = (bytes + 255) & ~size_t(255);
+  if (pinned_head + aligned > pinned_bytes) {
+    PGS_CUDA(cudaStreamSynchronize(stream));  // ring wrapped: wait for in-flight copies
+    pinned_head = 0;
+  }
+  char* slot = static_cast<char*>(pinned) + pinned_head;
+  pinned_head += aligned;
+  std::memcpy(slot, src, bytes);
+  PGS_CUDA(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, stream));
+}
+
+void Ctx::ensure_progress() {
+  if (h_progress) return;
+  void* h = nullptr;
+  PGS_CUDA(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+  void* d = nullptr;
+  PGS_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+  h_progress = static_cast<volatile int*>(h);
+  d_progress = static_cast<volatile int*>(d);
+  *h_progress = 0;
+  for (auto& e : loop_ev) PGS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+Desc& Cloud::add(const std::string& label, int span) {
+  Desc* d = find(label);
+  if (!d) {
+    descs.emplace_back();
+    d = &descs.back();
+    d->label = label;
+  }
+  d->span = span;
+  d->data.reset(ctx, (size_t)n * span);
+  d->data.zero();
+  return *d;
+}
+
+void Cloud::remove(const std::string& label) {
+  for (size_t i = 0; i < descs.size(); ++i)
+    if (descs[i].label == label) {
+      descs.erase(descs.begin() + i);
+      return;
+    }
+}
+
+std::unique_ptr<Cloud> Cloud::clone() const {
+  auto c = std::make_unique<Cloud>(ctx);
+  c->n = n;
+  c->feat.reset(ctx, (size_t)n);
+  if (n) PGS_CUDA(cudaMemcpyAsync(c->feat.p, feat.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (auto& d : descs) {
+    c->descs.emplace_back();
+    Desc& o = c->descs.back();
+    o.label = d.label;
+    o.span = d.span;
+    o.data.reset(ctx, (size_t)n * d.span);
+    if (n) PGS_CUDA(cudaMemcpyAsync(o.data.p, d.data.p, (size_t)n * d.span * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return c;
+}
+
+// DataPoints::concatenate (A.9): append columns; keep only descriptors present
+// in both clouds with equal span.
+void concatenate_cloud(Cloud& a, const Cloud& b) {
+  Ctx* ctx = a.ctx;
+  const int64_t na = a.n, nb = b.n;
+  DBuf<float4> nf(ctx, (size_t)(na + nb));
+  if (na) PGS_CUDA(cudaMemcpyAsync(nf.p, a.feat.p, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (nb) PGS_CUDA(cudaMemcpyAsync(nf.p + na, b.feat.p, (size_t)nb * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  a.feat = std::move(nf);
+  std::vector<Desc> kept;
+  for (auto& d : a.descs) {
+    const Desc* o = b.find(d.label);
+    if (!o || o->span != d.span) continue;
+    Desc nd;
+    nd.label = d.label;
+    nd.span = d.span;
+    nd.data.reset(ctx, (size_t)(na + nb) * d.span);
+    if (na) PGS_CUDA(cudaMemcpyAsync(nd.data.p, d.data.p, (size_t)na * d.span * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nb) PGS_CUDA(cudaMemcpyAsync(nd.data.p + (size_t)na * d.span, o->data.p, (size_t)nb * d.span * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    kept.push_back(std::move(nd));
+  }
+  a.descs = std::move(kept);
+  a.n = na + nb;
+}
+
+}  // namespace pgs

@@ -1,0 +1,189 @@
+// common.cuh — shared host/device plumbing for libpgslam_b200 (sm_100a only).
+//
+// Everything in this library is compiled with -fmad=false: the numeric
+// contract fixes the fp32 operation order of squared distances
+// and rigid transforms, and the fp64 solvers rely on +,-,*,/,sqrt only, so a
+// fused multiply-add anywhere on those paths would break bit-parity with the
+// CPU statement of the algorithm.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pgslam_b200.h"
+
+namespace pgs {
+
+// ---------------------------------------------------------------------------
+// errors: C++ exceptions inside the library, mapped to status codes at the ABI
+// (one code per libpointmatcher exception type, SURVEY.md §8b "Errors").
+// ---------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PGS_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess)                                                        \
+      throw ::pgs::Error(PGS_CUDA_ERROR, std::string(#expr) + ": " +              \
+                                             cudaGetErrorString(_e) + " at " +   \
+                                             __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define PGS_LAUNCH_CHECK() PGS_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------
+// context: one device, one stream.  Handles created from different contexts
+// are independent (pgslam-MT drives the localizer and the loop closer from two
+// host threads, LocalizerMT.hpp:47 / LoopCloserMT.hpp:41).
+// ---------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  std::string last_error;
+  uint64_t launches = 0;  // kernels launched through this context (bench.py gpu_launches)
+  bool profiling = false;
+  pgs_stage_times times{};
+  // pinned staging + mapped progress words for the ICP loop
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0, pinned_head = 0;
+  volatile int* h_progress = nullptr;  // mapped host word: set to 1 by the device when no pair is active
+  volatile int* d_progress = nullptr;  // device alias of h_progress
+  cudaEvent_t loop_ev[2] = {nullptr, nullptr};
+  void ensure_progress();
+
+  void* alloc(size_t bytes);
+  void free(void* p);
+  void upload_small(void* dst, const void* src, size_t bytes);
+  void sync() { PGS_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+static inline void ctx_count_launches(Ctx* ctx, int n) { ctx->launches += (uint64_t)n; }
+
+// RAII device buffer bound to a context's stream-ordered pool.
+template <typename T>
+struct DBuf {
+  Ctx* ctx = nullptr;
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() {}
+  DBuf(Ctx* c, size_t count) { reset(c, count); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); ctx = o.ctx; p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void reset(Ctx* c, size_t count) {
+    release();
+    ctx = c;
+    n = count;
+    p = static_cast<T*>(c->alloc((count ? count : 1) * sizeof(T)));
+  }
+  void release() {
+    if (p && ctx) ctx->free(p);
+    p = nullptr;
+    n = 0;
+  }
+  void zero() { PGS_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream)); }
+  void upload(const T* h, size_t count) {
+    PGS_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  void download(T* h, size_t count) const {
+    PGS_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// squared distance in the contract's order: ((dx*dx)+dy*dy)+dz*dz, fp32, no FMA
+__device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float px, float py, float pz) {
+  float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  float d = __fmul_rn(dx, dx);
+  d = __fadd_rn(d, __fmul_rn(dy, dy));
+  d = __fadd_rn(d, __fmul_rn(dz, dz));
+  return d;
+}
+
+// lower bound of dist2_rn over an axis-aligned box, same operation order, so
+// by monotonicity of IEEE rounding it never exceeds the computed distance to
+// any point inside the box.
+__device__ __forceinline__ float box_lb_rn(float qx, float qy, float qz, float lx, float ly, float lz,
+                                           float hx, float hy, float hz) {
+  float dx = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.f);
+  float dy = fmaxf(fmaxf(__fsub_rn(ly, qy), __fsub_rn(qy, hy)), 0.f);
+  float dz = fmaxf(fmaxf(__fsub_rn(lz, qz), __fsub_rn(qz, hz)), 0.f);
+  float d = __fmul_rn(dx, dx);
+  d = __fadd_rn(d, __fmul_rn(dy, dy));
+  d = __fadd_rn(d, __fmul_rn(dz, dz));
+  return d;
+}
+
+// 3x4 fp32 rigid transform, row r: (((T[r,0]*x)+T[r,1]*y)+T[r,2]*z)+T[r,3]
+struct Xf {
+  float m[12];  // row-major 3x4
+};
+__device__ __forceinline__ float3 xform_rn(const Xf& T, float x, float y, float z) {
+  float3 o;
+  o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.m[0], x), __fmul_rn(T.m[1], y)), __fmul_rn(T.m[2], z)), T.m[3]);
+  o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.m[4], x), __fmul_rn(T.m[5], y)), __fmul_rn(T.m[6], z)), T.m[7]);
+  o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T.m[8], x), __fmul_rn(T.m[9], y)), __fmul_rn(T.m[10], z)), T.m[11]);
+  return o;
+}
+__device__ __forceinline__ float3 rot_rn(const Xf& T, float x, float y, float z) {
+  float3 o;
+  o.x = __fadd_rn(__fadd_rn(__fmul_rn(T.m[0], x), __fmul_rn(T.m[1], y)), __fmul_rn(T.m[2], z));
+  o.y = __fadd_rn(__fadd_rn(__fmul_rn(T.m[4], x), __fmul_rn(T.m[5], y)), __fmul_rn(T.m[6], z));
+  o.z = __fadd_rn(__fadd_rn(__fmul_rn(T.m[8], x), __fmul_rn(T.m[9], y)), __fmul_rn(T.m[10], z));
+  return o;
+}
+
+// order-preserving float <-> uint mapping (for atomic min/max and radix keys)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 16-byte load that does not pollute L1 (read-once data)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+#endif  // __CUDACC__
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace pgs

@@ -1,0 +1,1309 @@
+// icp.cu — the ICP iteration loop on the device (SURVEY.md §3.3 "THE HOT LOOP";
+// ICP::compute / computeWithTransformedReference reached from LoopCloser.hpp:98
+// and Localizer.hpp:126).
+//
+// Per iteration, three kernels over all active pairs (blockIdx.y = pair):
+//   match      stepReading = T_iter * reading (fp32, fused, never stored) ->
+//              exact nearest neighbour in the reference index          (A7+A9)
+//   select     exact order statistic of the match distances by MSB radix
+//              select -> TrimmedDist / MedianDist limits                (A10)
+//   accumulate weights + ErrorElements + normal equations in one pass: the
+//              reference point and normal are gathered by match position, the
+//              6x6 / 3x3 sums are reduced in fp64 (warp shuffle -> block ->
+//              fixed-order sum over blocks), and the LAST block to finish
+//              solves, composes T_iter and runs the transformation checkers
+//              on one thread                                       (A11-A14)
+// so an iteration needs no host round trip; the host only polls a mapped flag
+// to stop launching once every pair has converged.
+#include "icp.cuh"
+
+#include <cmath>
+#include <cstring>
+
+#include "knn.cuh"
+#include "solve.cuh"
+
+namespace pgs {
+
+namespace {
+
+constexpr float kInfF = __builtin_inff();
+
+__host__ __device__ inline int tri(int c, int r) { return c * (c + 1) / 2 + r; }  // r <= c
+
+// ---------------------------------------------------------------------------
+// per-pair accumulation of one weighted match (A.5 / A.7), all in fp64
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void accumulate_match(double* acc, int minimizer, const float3 pf, const float4 qf,
+                                                 const float3 nf, double w) {
+  const double p[3] = {(double)pf.x, (double)pf.y, (double)pf.z};
+  if (minimizer == MIN_P2POINT) {
+    const double q[3] = {(double)qf.x, (double)qf.y, (double)qf.z};
+    acc[0] += w;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { acc[1 + d] += w * p[d]; acc[4 + d] += w * q[d]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += w * q[r] * p[c];
+    double dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+    acc[27] += sqrt(dx * dx + dy * dy + dz * dz);
+  } else {
+    const double n[3] = {(double)nf.x, (double)nf.y, (double)nf.z};
+    double F[6];
+    F[0] = p[1] * n[2] - p[2] * n[1];
+    F[1] = p[2] * n[0] - p[0] * n[2];
+    F[2] = p[0] * n[1] - p[1] * n[0];
+    F[3] = n[0]; F[4] = n[1]; F[5] = n[2];
+    double e = (p[0] - (double)qf.x) * n[0] + (p[1] - (double)qf.y) * n[1] + (p[2] - (double)qf.z) * n[2];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double wf = w * F[c];
+#pragma unroll
+      for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += wf * F[r];
+      acc[21 + c] -= wf * e;
+    }
+    acc[27] += w * (e * e);
+  }
+  acc[28] += 1.0;
+  acc[29] += w;
+}
+
+// A.6 per-pair terms of the Censi covariance; acc2[0..20] = H, [21..41] = D D^T
+__device__ __forceinline__ void accumulate_cov(double* acc2, const float3 pf, const float4 qf, const float3 nf,
+                                               double alpha, double beta, double gamma, const double* t) {
+  double p[3] = {(double)pf.x, (double)pf.y, (double)pf.z}, q[3] = {(double)qf.x, (double)qf.y, (double)qf.z};
+  double n[3] = {(double)nf.x, (double)nf.y, (double)nf.z};
+  double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  double rp = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  double rq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (!(nn > 0.0) || !(rp > 0.0) || !(rq > 0.0)) return;
+  for (int d = 0; d < 3; ++d) n[d] = n[d] / nn;
+  double dp[3] = {p[0] / rp, p[1] / rp, p[2] / rp};
+  double dq[3] = {q[0] / rq, q[1] / rq, q[2] / rq};
+  double na = n[2] * dp[1] - n[1] * dp[2];
+  double nb = n[0] * dp[2] - n[2] * dp[0];
+  double ng = n[1] * dp[0] - n[0] * dp[1];
+  double E = n[0] * (p[0] - gamma * p[1] + beta * p[2] + t[0] - q[0]);
+  E += n[1] * (gamma * p[0] + p[1] - alpha * p[2] + t[1] - q[1]);
+  E += n[2] * (-beta * p[0] + alpha * p[1] + p[2] + t[2] - q[2]);
+  double Np = n[0] * (dp[0] - gamma * dp[1] + beta * dp[2]);
+  Np += n[1] * (gamma * dp[0] + dp[1] - alpha * dp[2]);
+  Np += n[2] * (-beta * dp[0] + alpha * dp[1] + dp[2]);
+  double Nq = -(n[0] * dq[0] + n[1] * dq[1] + n[2] * dq[2]);
+  double g[6] = {n[0], n[1], n[2], rp * na, rp * nb, rp * ng};
+  double en = E + rp * Np;
+  double u[6] = {n[0] * Np, n[1] * Np, n[2] * Np, na * en, nb * en, ng * en};
+  double v[6] = {n[0] * Nq, n[1] * Nq, n[2] * Nq, rq * na * Nq, rq * nb * Nq, rq * ng * Nq};
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int r = 0; r <= c; ++r) {
+      acc2[c * (c + 1) / 2 + r] += g[c] * g[r];
+      acc2[21 + c * (c + 1) / 2 + r] += u[c] * u[r] + v[c] * v[r];
+    }
+}
+
+__device__ void xf_from_T_dev(const double* T, Xf& x) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) x.m[r * 4 + c] = (float)T[c * 4 + r];
+}
+
+__device__ void chk_push(PairState& st, const double* T) {
+  if (st.nhist == kChkHist) {
+    for (int i = 0; i + 1 < kChkHist; ++i) {
+      for (int d = 0; d < 4; ++d) st.q[i][d] = st.q[i + 1][d];
+      for (int d = 0; d < 3; ++d) st.t[i][d] = st.t[i + 1][d];
+    }
+    st.nhist--;
+  }
+  quat_from_T(T, st.q[st.nhist]);
+  st.t[st.nhist][0] = T[12]; st.t[st.nhist][1] = T[13]; st.t[st.nhist][2] = T[14];
+  st.nhist++;
+}
+
+__device__ void pair_finished(int* n_active, volatile int* h_done) {
+  int left = atomicSub(n_active, 1) - 1;
+  if (left == 0) {
+    *h_done = 1;
+    __threadfence_system();
+  }
+}
+
+// ErrorMinimizer::compute + T_iter update + TransformationCheckers (one thread)
+__device__ void finish_iteration(PairState& st, const IcpParams& P, const double* acc, int* n_active,
+                                 volatile int* h_done) {
+  st.kept = acc[28];
+  st.wsum = acc[29];
+  st.resid = acc[27];
+  if (!(acc[28] > 0.0)) {  // "no point to minimize"
+    st.status = PGS_CONVERGENCE_ERROR;
+    st.active = 0;
+    pair_finished(n_active, h_done);
+    return;
+  }
+  double Tinc[16];
+  if (P.minimizer == MIN_P2POINT) {
+    const double W = acc[0];
+    double mp[3], mq[3], M[9];
+    for (int d = 0; d < 3; ++d) { mp[d] = acc[1 + d] / W; mq[d] = acc[4 + d] / W; }
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) M[c * 3 + r] = acc[7 + c * 3 + r] - W * mq[r] * mp[c];
+    double U[9], S[3], V[9], R[9];
+    svd3(M, U, S, V);
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += U[k * 3 + r] * V[k * 3 + c];
+        R[c * 3 + r] = s;
+      }
+    double det = R[0] * (R[4] * R[8] - R[7] * R[5]) - R[3] * (R[1] * R[8] - R[7] * R[2]) +
+                 R[6] * (R[1] * R[5] - R[4] * R[2]);
+    if (det < 0.0) {
+      for (int r = 0; r < 3; ++r) V[6 + r] = -V[6 + r];
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) {
+          double s = 0.0;
+          for (int k = 0; k < 3; ++k) s += U[k * 3 + r] * V[k * 3 + c];
+          R[c * 3 + r] = s;
+        }
+    }
+    m4_identity(Tinc);
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) Tinc[c * 4 + r] = R[c * 3 + r];
+    for (int r = 0; r < 3; ++r) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += R[k * 3 + r] * mp[k];
+      Tinc[12 + r] = mq[r] - s;
+    }
+  } else {
+    double A[36], b[6], x[6];
+    for (int c = 0; c < 6; ++c) {
+      for (int r = 0; r <= c; ++r) {
+        A[c * 6 + r] = acc[tri(c, r)];
+        A[r * 6 + c] = acc[tri(c, r)];
+      }
+      b[c] = acc[21 + c];
+    }
+    solve6(A, b, x);
+    angle_axis_to_T(x, Tinc);
+  }
+  for (int i = 0; i < 16; ++i) { st.T_prev[i] = st.T_iter[i]; st.T_inc[i] = Tinc[i]; }
+  st.xf_prev = st.xf;
+  m4_mul(Tinc, st.T_iter, st.T_iter);
+  st.iterations++;
+
+  bool iterate = true;
+  int status = PGS_OK;
+  if (P.max_iterations > 0) {
+    st.counter++;
+    if (st.counter >= P.max_iterations) { iterate = false; st.max_reached = 1; }
+  }
+  chk_push(st, st.T_iter);
+  if (P.has_diff) {
+    const int sl = P.smooth_length;
+    if (st.nhist > sl) {
+      double c0 = 0.0, c1 = 0.0;
+      for (int i = st.nhist - 1; i >= st.nhist - sl; --i) {
+        c0 += fabs(quat_angular_distance(st.q[i], st.q[i - 1]));
+        double dx = st.t[i][0] - st.t[i - 1][0], dy = st.t[i][1] - st.t[i - 1][1], dz = st.t[i][2] - st.t[i - 1][2];
+        c1 += sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      c0 = c0 / (double)sl;
+      c1 = c1 / (double)sl;
+      if (isnan(c0) || isnan(c1)) status = PGS_CONVERGENCE_ERROR;
+      else if (c0 < P.min_diff_rot && c1 < P.min_diff_trans) iterate = false;
+    }
+  }
+  if (P.has_bound) {
+    double qn[4];
+    quat_from_T(st.T_iter, qn);
+    double dx = st.T_iter[12] - st.t0[0], dy = st.T_iter[13] - st.t0[1], dz = st.T_iter[14] - st.t0[2];
+    if (quat_angular_distance(qn, st.q0) > P.max_rot || sqrt(dx * dx + dy * dy + dz * dz) > P.max_trans)
+      status = PGS_CONVERGENCE_ERROR;
+  }
+  if (st.iterations >= P.hard_iteration_cap) { iterate = false; st.max_reached = 1; }
+  if (status == PGS_OK && iterate) {
+    const double* T = st.T_iter;
+    double det = T[0] * (T[5] * T[10] - T[9] * T[6]) - T[4] * (T[1] * T[10] - T[9] * T[2]) +
+                 T[8] * (T[1] * T[6] - T[5] * T[2]);
+    if (!(fabs(1.0 - det) <= 0.001)) status = PGS_TRANSFORMATION_ERROR;
+  }
+  xf_from_T_dev(st.T_iter, st.xf);
+  if (status != PGS_OK) st.status = status;
+  if (status != PGS_OK || !iterate) {
+    st.active = 0;
+    pair_finished(n_active, h_done);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mean_kernel(const float4* const* __restrict__ pts, const int* __restrict__ ns, double* __restrict__ partials,
+            unsigned* __restrict__ tickets, float* __restrict__ shift /*4 per job*/) {
+  __shared__ double sh[8][3];
+  __shared__ bool last;
+  const int b = blockIdx.y;
+  const int n = ns[b];
+  const float4* p = pts[b];
+  double s[3] = {0.0, 0.0, 0.0};
+  // contiguous slice per block, strided inside: any order is fine in fp64 as
+  // long as it is FIXED, which it is (grid size depends only on the batch)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z;
+  }
+  for (int d = 0; d < 3; ++d) s[d] = warp_sum(s[d]);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[w][0] = s[0]; sh[w][1] = s[1]; sh[w][2] = s[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&tickets[b], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (unsigned j = 0; j < gridDim.x; ++j) t += __ldcg(&partials[((size_t)b * gridDim.x + j) * 3 + threadIdx.x]);
+    shift[4 * b + threadIdx.x] = n > 0 ? (float)(t / (double)n) : 0.f;
+  }
+  if (threadIdx.x == 3) shift[4 * b + 3] = 0.f;
+  if (threadIdx.x == 0) tickets[b] = 0;
+}
+
+__global__ void shift_points_kernel(float4* __restrict__ pts, int n, const float* __restrict__ shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  pts[i] = make_float4(__fsub_rn(p.x, shift[0]), __fsub_rn(p.y, shift[1]), __fsub_rn(p.z, shift[2]), p.w);
+}
+
+// per-pair state initialisation: pose algebra in fp64 on the device so that the
+// reference mean never has to visit the host
+__global__ void init_state_kernel(PairState* __restrict__ states, const double* __restrict__ T_refIn_refMean,
+                                  int n_pairs) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  PairState& st = states[p];
+  for (int i = 0; i < 16; ++i) st.T_refIn_refMean[i] = T_refIn_refMean[16 * p + i];
+  double inv[16];
+  m4_rigid_inv(st.T_refIn_refMean, inv);
+  m4_mul(inv, st.T_init, st.T_refMean_dataIn);
+  xf_from_T_dev(st.T_refMean_dataIn, st.xf0);
+  m4_identity(st.T_iter);
+  m4_identity(st.T_prev);
+  m4_identity(st.T_inc);
+  xf_from_T_dev(st.T_iter, st.xf);
+  st.xf_prev = st.xf;
+  st.iterations = 0;
+  st.max_reached = 0;
+  st.counter = 0;
+  st.nhist = 0;
+  chk_push(st, st.T_iter);
+  for (int d = 0; d < 4; ++d) st.q0[d] = st.q[0][d];
+  for (int d = 0; d < 3; ++d) st.t0[d] = st.t[0][d];
+  st.ticket = 0;
+  st.ticket2 = 0;
+  st.kept = st.wsum = st.resid = st.overlap = 0.0;
+  for (int i = 0; i < 36; ++i) st.cov[i] = 0.0;
+  st.lim_lo = -kInfF;
+  st.lim_hi = kInfF;
+}
+
+// T_refIn_refMean from the device-side mean (identity + translation)
+__global__ void mean_pose_kernel(const float* __restrict__ shift, double* __restrict__ T, int n_jobs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_jobs) return;
+  double* M = T + 16 * b;
+  m4_identity(M);
+  M[12] = (double)shift[4 * b]; M[13] = (double)shift[4 * b + 1]; M[14] = (double)shift[4 * b + 2];
+}
+
+struct PreJob {
+  float4* feat;
+  float* normals;
+  float* obs;
+  int n;
+};
+// transformations.apply(reading, T_refMean_dataIn) for every pair
+__global__ void __launch_bounds__(256)
+pretransform_kernel(const PreJob* __restrict__ jobs, const PairState* __restrict__ states) {
+  const PreJob job = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= job.n) return;
+  const Xf T = states[blockIdx.y].xf0;
+  float4 p = job.feat[i];
+  float3 o = xform_rn(T, p.x, p.y, p.z);
+  job.feat[i] = make_float4(o.x, o.y, o.z, p.w);
+  if (job.normals) {
+    float3 v = rot_rn(T, job.normals[3 * i], job.normals[3 * i + 1], job.normals[3 * i + 2]);
+    job.normals[3 * i] = v.x; job.normals[3 * i + 1] = v.y; job.normals[3 * i + 2] = v.z;
+  }
+  if (job.obs) {
+    float3 v = rot_rn(T, job.obs[3 * i], job.obs[3 * i + 1], job.obs[3 * i + 2]);
+    job.obs[3 * i] = v.x; job.obs[3 * i + 1] = v.y; job.obs[3 * i + 2] = v.z;
+  }
+}
+
+// descriptor rows re-ordered to the index' sorted order (float4 per point)
+__global__ void __launch_bounds__(256)
+gather_vec3_sorted_kernel(const float4* __restrict__ sorted_pts, int n, const float* __restrict__ src, int span,
+                          float4* __restrict__ out4, float* __restrict__ out1) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int o = __float_as_int(sorted_pts[j].w);
+  if (span == 3) out4[j] = make_float4(src[3 * o], src[3 * o + 1], src[3 * o + 2], 0.f);
+  else out1[j] = src[o];
+}
+
+__global__ void __launch_bounds__(128)
+match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_r) return;
+  const Xf T = st.xf;
+  float4 r = v.reading[i];
+  float3 q = xform_rn(T, r.x, r.y, r.z);
+  Best1 acc;
+  acc.init();
+  if (st.iterations > 0) {
+    // temporal coherence: last iteration's match is an excellent first bound
+    int pp = v.match_pos[i];
+    if (pp >= 0) {
+      float4 c = v.tree.pts[pp];
+      float d = dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
+      if (d <= maxr2) acc.offer(d, __float_as_int(c.w), pp);
+    }
+  }
+  knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
+  v.match_pos[i] = acc.pos;
+  v.match_d2[i] = acc.d;
+}
+
+// exact quantile(s) of the valid match distances: 4-pass MSB radix select on
+// the fp32 bit patterns (non-negative floats order like unsigned ints)
+__global__ void __launch_bounds__(1024)
+select_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int* n_active,
+              volatile int* h_done) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_mask, s_fail;
+  __shared__ unsigned long long s_rank;
+  PairState& st = states[blockIdx.x];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31;
+  float hi = P.fixed_hi, lo = P.fixed_lo;
+  for (int jq = 0; jq < P.n_quant; ++jq) {
+    if (tid == 0) { s_prefix = 0; s_mask = 0; s_fail = 0; s_rank = 0; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix, mask = s_mask;
+      for (int base = 0; base < v.n_r; base += 1024) {
+        const int i = base + tid;
+        unsigned u = 0;
+        bool valid = false;
+        if (i < v.n_r) {
+          u = __float_as_uint(v.match_d2[i]);
+          // getDistsQuantile: dist != inf and dist > 0 (A.3)
+          valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
+        }
+        unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          unsigned d = (u >> shift) & 255u;
+          unsigned m = __match_any_sync(act, d);
+          if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long rank = s_rank;
+        if (pass == 0) {
+          unsigned long long M = 0;
+          for (int d = 0; d < 256; ++d) M += hist[d];
+          if (M == 0) s_fail = 1;
+          const double q = P.q_ratio[jq];
+          rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
+          if (M && rank >= M) rank = M - 1;
+        }
+        unsigned long long cum = 0;
+        int d = 0;
+        for (; d < 255; ++d) {
+          if (cum + hist[d] > rank) break;
+          cum += hist[d];
+        }
+        s_rank = rank - cum;
+        s_prefix = prefix | ((unsigned)d << shift);
+        s_mask = mask | (255u << shift);
+      }
+      __syncthreads();
+      if (s_fail) break;
+    }
+    if (s_fail) {
+      if (tid == 0) {  // "no outlier to filter"
+        st.status = PGS_CONVERGENCE_ERROR;
+        st.active = 0;
+        pair_finished(n_active, h_done);
+      }
+      return;
+    }
+    float limit = __fmul_rn(P.q_factor[jq], __uint_as_float(s_prefix));
+    hi = fminf(hi, limit);
+    __syncthreads();
+  }
+  if (tid == 0) { st.lim_lo = lo; st.lim_hi = hi; }
+}
+
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int* n_active,
+                  volatile int* h_done) {
+  __shared__ double sh[8][kAcc];
+  __shared__ double tot[kAcc];
+  __shared__ bool last;
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const Xf T = st.xf;
+  const float lo = st.lim_lo, hi = st.lim_hi;
+  double acc[kAcc];
+#pragma unroll
+  for (int j = 0; j < kAcc; ++j) acc[j] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += gridDim.x * blockDim.x) {
+    const int pos = v.match_pos[i];
+    const float d = v.match_d2[i];
+    // ErrorElements skips dist == inf; OutlierFilters weights are 0/1 here
+    bool use = pos >= 0 && d < kInfF;
+    if (P.has_outliers) use = use && d <= hi && d >= lo;
+    if (!use) continue;
+    float4 r = v.reading[i];
+    float3 p = xform_rn(T, r.x, r.y, r.z);
+    float4 q = v.tree.pts[pos];
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (P.minimizer != MIN_P2POINT) {
+      float4 n4 = v.ref_normals[pos];
+      n = make_float3(n4.x, n4.y, n4.z);
+    }
+    accumulate_match(acc, P.minimizer, p, q, n, 1.0);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 30; ++j) {
+    double s = warp_sum(acc[j]);
+    if (lane == 0) sh[w][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 30) {
+    double t = 0.0;
+    for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    v.partials[(size_t)blockIdx.x * kAcc2 + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 30) {
+    double t = 0.0;
+    for (unsigned j = 0; j < gridDim.x; ++j) t += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st.ticket = 0;
+    for (int j = 0; j < 30; ++j) st.acc[j] = tot[j];
+    finish_iteration(st, P, tot, n_active, h_done);
+  }
+}
+
+// after the loop: covariance (WithCov) and the sensor-noise overlap, from the
+// LAST iteration's matches, limits and transform (what lastErrorElements holds)
+__global__ void __launch_bounds__(256)
+final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P) {
+  __shared__ double sh[8][kAcc2];
+  __shared__ bool last;
+  PairState& st = states[blockIdx.y];
+  if (st.status != PGS_OK || st.iterations == 0) return;
+  const PairView v = views[blockIdx.y];
+  const Xf T = st.xf_prev;
+  const float lo = st.lim_lo, hi = st.lim_hi;
+  const bool want_cov = P.minimizer == MIN_P2PLANE_COV;
+  const bool want_overlap = v.rd_normals != nullptr && v.rd_noise != nullptr && P.minimizer != MIN_P2POINT;
+  double alpha = 0, beta = 0, gamma = 0, t[3] = {0, 0, 0};
+  if (want_cov) {
+    const double* Ti = st.T_inc;
+    beta = -asin(Ti[2]);
+    alpha = atan2(Ti[6], Ti[10]);
+    double cb = cos(beta);
+    gamma = atan2(Ti[1] / cb, Ti[0] / cb);
+    t[0] = Ti[12]; t[1] = Ti[13]; t[2] = Ti[14];
+  }
+  double acc[kAcc2];
+#pragma unroll
+  for (int j = 0; j < kAcc2; ++j) acc[j] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += gridDim.x * blockDim.x) {
+    const int pos = v.match_pos[i];
+    const float d = v.match_d2[i];
+    bool use = pos >= 0 && d < kInfF;
+    if (P.has_outliers) use = use && d <= hi && d >= lo;
+    if (!use) continue;
+    float4 r = v.reading[i];
+    float3 p = xform_rn(T, r.x, r.y, r.z);
+    float4 q = v.tree.pts[pos];
+    if (want_cov) {
+      float4 n4 = v.ref_normals[pos];
+      accumulate_cov(acc, p, q, make_float3(n4.x, n4.y, n4.z), alpha, beta, gamma, t);
+    }
+    if (want_overlap) {
+      float4 rn = v.rd_normals[i];
+      float3 nr = rot_rn(T, rn.x, rn.y, rn.z);
+      double n[3] = {(double)nr.x, (double)nr.y, (double)nr.z};
+      double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      double e = ((double)p.x - (double)q.x) * (n[0] / nn) + ((double)p.y - (double)q.y) * (n[1] / nn) +
+                 ((double)p.z - (double)q.z) * (n[2] / nn);
+      if (fabs(e) < (double)v.rd_noise[i]) acc[42] += 1.0;
+    }
+    acc[43] += 1.0;
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kAcc2; ++j) {
+    double s = warp_sum(acc[j]);
+    if (lane == 0) sh[w][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc2) {
+    double s = 0.0;
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    v.partials[(size_t)blockIdx.x * kAcc2 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket2, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < kAcc2) {
+    double s = 0.0;
+    for (unsigned j = 0; j < gridDim.x; ++j) s += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
+    st.acc2[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) st.ticket2 = 0;
+}
+
+__global__ void finish_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P,
+                              int n_pairs) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  PairState& st = states[p];
+  const PairView v = views[p];
+  double tmp[16];
+  m4_mul(st.T_iter, st.T_refMean_dataIn, tmp);
+  m4_mul(st.T_refIn_refMean, tmp, st.T_out);
+  if (st.status != PGS_OK || st.iterations == 0) return;
+  const double denom = (double)v.n_r;  // k == 1
+  const bool want_overlap = v.rd_normals != nullptr && v.rd_noise != nullptr && P.minimizer != MIN_P2POINT;
+  st.overlap = want_overlap ? (st.acc2[43] > 0.0 ? st.acc2[42] / st.acc2[43] : 0.0) : st.wsum / denom;
+  if (P.minimizer == MIN_P2PLANE_COV) {
+    double H[36], DD[36], Hi[36], t1[36];
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r <= c; ++r) {
+        H[c * 6 + r] = H[r * 6 + c] = st.acc2[tri(c, r)];
+        DD[c * 6 + r] = DD[r * 6 + c] = st.acc2[21 + tri(c, r)];
+      }
+    inv6_sym(H, Hi);
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += Hi[k * 6 + r] * DD[c * 6 + k];
+        t1[c * 6 + r] = s;
+      }
+    const double s2 = P.sensor_std_dev * P.sensor_std_dev;
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += t1[k * 6 + r] * Hi[c * 6 + k];
+        st.cov[c * 6 + r] = s2 * s;
+      }
+  }
+}
+
+// ---- fine-grained module kernels (explicit Matches / OutlierWeights) -------
+__global__ void __launch_bounds__(256)
+weights_kernel(const float* __restrict__ d2, int64_t nk, int has_outliers, float lo, float hi, float* __restrict__ w) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk) return;
+  float d = d2[i];
+  // TrimmedDist/MaxDist/MedianDist: dist <= limit; MinDist: dist >= limit;
+  // empty filter list: 1 unless dist == inf (A.3)
+  w[i] = has_outliers ? ((d <= hi && d >= lo) ? 1.f : 0.f) : ((d == kInfF) ? 0.f : 1.f);
+}
+
+struct ExplicitJob {
+  const float4* reading;
+  const float4* reference;
+  const float* ref_normals;  // 3 per point or null
+  const float* rd_normals;
+  const float* rd_noise;
+  const int32_t* ids;
+  const float* d2;
+  const float* w;
+  int64_t n_r;
+  int k;
+  double* partials;
+};
+
+__global__ void __launch_bounds__(256)
+explicit_accumulate_kernel(ExplicitJob job, int minimizer, int pass, double alpha, double beta, double gamma,
+                           double t0, double t1, double t2) {
+  __shared__ double sh[8][kAcc2];
+  double acc[kAcc2];
+#pragma unroll
+  for (int j = 0; j < kAcc2; ++j) acc[j] = 0.0;
+  const double t[3] = {t0, t1, t2};
+  const int64_t total = job.n_r * job.k;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (int64_t)gridDim.x * blockDim.x) {
+    const float d = job.d2[m];
+    const float w = job.w[m];
+    if (d == kInfF || w == 0.f) continue;
+    const int64_t i = m / job.k;
+    const int id = job.ids[m];
+    float4 r = job.reading[i];
+    float4 q = job.reference[id];
+    float3 p = make_float3(r.x, r.y, r.z);
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (job.ref_normals) n = make_float3(job.ref_normals[3 * id], job.ref_normals[3 * id + 1], job.ref_normals[3 * id + 2]);
+    if (pass == 0) {
+      accumulate_match(acc, minimizer, p, q, n, (double)w);
+    } else {
+      if (minimizer == MIN_P2PLANE_COV) accumulate_cov(acc, p, q, n, alpha, beta, gamma, t);
+      if (job.rd_normals && job.rd_noise && minimizer != MIN_P2POINT) {
+        double nr[3] = {(double)job.rd_normals[3 * i], (double)job.rd_normals[3 * i + 1], (double)job.rd_normals[3 * i + 2]};
+        double nn = sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+        double e = ((double)p.x - (double)q.x) * (nr[0] / nn) + ((double)p.y - (double)q.y) * (nr[1] / nn) +
+                   ((double)p.z - (double)q.z) * (nr[2] / nn);
+        if (fabs(e) < (double)job.rd_noise[i]) acc[42] += 1.0;
+      }
+      acc[43] += 1.0;
+    }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < kAcc2; ++j) {
+    double s = warp_sum(acc[j]);
+    if (lane == 0) sh[w][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc2) {
+    double s = 0.0;
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    job.partials[(size_t)blockIdx.x * kAcc2 + threadIdx.x] = s;
+  }
+}
+
+// single-block quantile for the fine-grained OutlierFilters path
+__global__ void __launch_bounds__(1024)
+quantile_kernel(const float* __restrict__ d2, int64_t nk, double q, float* __restrict__ out, int* __restrict__ fail) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_mask, s_fail;
+  __shared__ unsigned long long s_rank;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) { s_prefix = 0; s_mask = 0; s_fail = 0; s_rank = 0; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, mask = s_mask;
+    for (int64_t base = 0; base < nk; base += 1024) {
+      const int64_t i = base + tid;
+      unsigned u = 0;
+      bool valid = false;
+      if (i < nk) {
+        u = __float_as_uint(d2[i]);
+        valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
+      }
+      unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        unsigned d = (u >> shift) & 255u;
+        unsigned m = __match_any_sync(act, d);
+        if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long rank = s_rank;
+      if (pass == 0) {
+        unsigned long long M = 0;
+        for (int d = 0; d < 256; ++d) M += hist[d];
+        if (M == 0) s_fail = 1;
+        rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
+        if (M && rank >= M) rank = M - 1;
+      }
+      unsigned long long cum = 0;
+      int d = 0;
+      for (; d < 255; ++d) {
+        if (cum + hist[d] > rank) break;
+        cum += hist[d];
+      }
+      s_rank = rank - cum;
+      s_prefix = prefix | ((unsigned)d << shift);
+      s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+    if (s_fail) break;
+  }
+  if (tid == 0) {
+    *fail = (int)s_fail;
+    *out = __uint_as_float(s_prefix);
+  }
+}
+
+__global__ void solve_only_kernel(PairState* st, const double* acc, IcpParams P, int* n_active,
+                                  volatile int* h_done) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) finish_iteration(*st, P, acc, n_active, h_done);
+}
+
+void solve_only_kernel_launch(Ctx* ctx, PairState* st, const double* acc, const IcpParams& prm, int* n_active) {
+  solve_only_kernel<<<1, 32, 0, ctx->stream>>>(st, acc, prm, n_active, ctx->d_progress);
+  ctx_count_launches(ctx, 2);
+}
+
+__global__ void __launch_bounds__(256)
+ratio_kernel(const float* __restrict__ d2, const float* __restrict__ w, int64_t nk, double* __restrict__ out) {
+  double kept = 0.0, wsum = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += (int64_t)gridDim.x * blockDim.x) {
+    if (d2[i] != kInfF && w[i] != 0.f) { kept += 1.0; wsum += (double)w[i]; }
+  }
+  kept = warp_sum(kept);
+  wsum = warp_sum(wsum);
+  if ((threadIdx.x & 31) == 0) {  // counts of 0/1 weights: exact in fp64 in any order
+    atomicAdd(out, kept);
+    atomicAdd(out + 1, wsum);
+  }
+}
+
+}  // namespace
+
+void weights_ratio_device(Ctx* ctx, const float* d_d2, const float* d_w, int64_t nk, double* kept, double* wsum) {
+  DBuf<double> out(ctx, 2);
+  out.zero();
+  if (nk > 0) {
+    ratio_kernel<<<std::min(ceil_div(nk, 1024), 296), 256, 0, ctx->stream>>>(d_d2, d_w, nk, out.p);
+    ctx_count_launches(ctx, 1);
+  }
+  double h[2];
+  out.download(h, 2);
+  ctx->sync();
+  *kept = h[0];
+  *wsum = h[1];
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p) {
+  p->has_outliers = 0;
+  p->n_quant = 0;
+  p->fixed_hi = kInfF;
+  p->fixed_lo = -kInfF;
+  for (auto& f : filters) {
+    if (f.name == "NullOutlierFilter") {
+      // weight 1 for everything; combined with others it is a no-op.  Alone it
+      // keeps even dist == inf, which ErrorElements then skips anyway.
+      p->has_outliers = 1;
+      continue;
+    }
+    p->has_outliers = 1;
+    if (f.name == "TrimmedDistOutlierFilter" || f.name == "MedianDistOutlierFilter") {
+      if (p->n_quant == kMaxQuant) throw Error(PGS_INVALID_PARAMETER, "too many quantile-based outlier filters");
+      const bool trimmed = f.name[0] == 'T';
+      p->q_ratio[p->n_quant] = trimmed ? f.real("ratio") : 0.5;
+      p->q_factor[p->n_quant] = trimmed ? 1.0f : (float)f.real("factor");
+      p->n_quant++;
+    } else if (f.name == "MaxDistOutlierFilter") {
+      float m = (float)f.real("maxDist");
+      p->fixed_hi = std::min(p->fixed_hi, m * m);
+    } else if (f.name == "MinDistOutlierFilter") {
+      float m = (float)f.real("minDist");
+      p->fixed_lo = std::max(p->fixed_lo, m * m);
+    } else {
+      throw Error(PGS_INVALID_ELEMENT, "OutlierFilter " + f.name + " has no device implementation");
+    }
+  }
+}
+
+IcpParams params_from_chain(const ChainConfig& cfg) {
+  IcpParams p;
+  std::memset(&p, 0, sizeof(p));
+  const std::string& mn = cfg.minimizer.name;
+  if (mn == "PointToPlaneErrorMinimizer") p.minimizer = MIN_P2PLANE;
+  else if (mn == "PointToPlaneWithCovErrorMinimizer") p.minimizer = MIN_P2PLANE_COV;
+  else if (mn == "PointToPointErrorMinimizer") p.minimizer = MIN_P2POINT;
+  else throw Error(PGS_INVALID_ELEMENT, "ErrorMinimizer " + mn + " has no device implementation");
+  if (p.minimizer != MIN_P2POINT && (cfg.minimizer.flag("force2D") || cfg.minimizer.flag("force4DOF")))
+    throw Error(PGS_INVALID_PARAMETER, mn + ": force2D / force4DOF are not supported");
+  p.sensor_std_dev = p.minimizer == MIN_P2PLANE_COV ? cfg.minimizer.real("sensorStdDev") : 0.01;
+  p.max_iterations = 0;
+  p.has_diff = 0;
+  p.has_bound = 0;
+  p.smooth_length = 3;
+  for (auto& c : cfg.checkers) {
+    if (c.name == "CounterTransformationChecker") {
+      p.max_iterations = (int)c.integer("maxIterationCount");
+      if (p.max_iterations <= 0) p.max_iterations = 1;
+    } else if (c.name == "DifferentialTransformationChecker") {
+      p.has_diff = 1;
+      p.min_diff_rot = c.real("minDiffRotErr");
+      p.min_diff_trans = c.real("minDiffTransErr");
+      p.smooth_length = (int)c.integer("smoothLength");
+    } else if (c.name == "BoundTransformationChecker") {
+      p.has_bound = 1;
+      p.max_rot = c.real("maxRotationNorm");
+      p.max_trans = c.real("maxTranslationNorm");
+    }
+  }
+  p.hard_iteration_cap = p.max_iterations > 0 ? p.max_iterations : 1000;
+  outlier_limits_params(cfg.outlier_filters, &p);
+  if (cfg.matcher.name != "KDTreeMatcher") throw Error(PGS_INVALID_ELEMENT, "Matcher " + cfg.matcher.name + " has no device implementation");
+  if (cfg.matcher.integer("knn") != 1)
+    throw Error(PGS_INVALID_PARAMETER, "the fused ICP loop supports KDTreeMatcher knn = 1 (use the Matcher module for knn > 1)");
+  float md = (float)cfg.matcher.real("maxDist");
+  p.max_r2 = std::isinf(md) ? kInfF : md * md;
+  if (!cfg.reading_step_filters.empty())
+    throw Error(PGS_INVALID_PARAMETER, "readingStepDataPointsFilters are not supported by the fused ICP loop");
+  return p;
+}
+
+IcpEngine::IcpEngine(Ctx* ctx, const ChainConfig& cfg) : ctx_(ctx), cfg_(cfg) { params_ = params_from_chain(cfg); }
+
+void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bool centre_first,
+                                   std::vector<std::unique_ptr<PreparedRef>>& out) {
+  Ctx* ctx = ctx_;
+  cudaStream_t s = ctx->stream;
+  const int B = (int)refs.size();
+  std::vector<Cloud*> rp(B);
+  for (int b = 0; b < B; ++b) rp[b] = refs[b].get();
+  DBuf<float> shift(ctx, (size_t)4 * B);
+  DBuf<double> Tmean(ctx, (size_t)16 * B);
+  auto compute_mean = [&]() {
+    std::vector<const float4*> pts(B);
+    std::vector<int> ns(B);
+    int max_n = 0;
+    for (int b = 0; b < B; ++b) { pts[b] = rp[b]->feat.p; ns[b] = (int)rp[b]->n; max_n = std::max(max_n, ns[b]); }
+    DBuf<const float4*> d_pts(ctx, B);
+    DBuf<int> d_n(ctx, B);
+    ctx->upload_small(d_pts.p, pts.data(), sizeof(float4*) * B);
+    ctx->upload_small(d_n.p, ns.data(), sizeof(int) * B);
+    const int nb = std::max(1, std::min(ceil_div(max_n, 2048), 64));
+    DBuf<double> partials(ctx, (size_t)B * nb * 3);
+    DBuf<unsigned> tickets(ctx, B);
+    tickets.zero();
+    mean_kernel<<<dim3(nb, B), 256, 0, s>>>(d_pts.p, d_n.p, partials.p, tickets.p, shift.p);
+    mean_pose_kernel<<<ceil_div(B, 64), 64, 0, s>>>(shift.p, Tmean.p, B);
+    ctx_count_launches(ctx, 2);
+  };
+  if (centre_first) {
+    // ICPSequence::setMap: mean-centre, THEN reference filters (A16)
+    compute_mean();
+    for (int b = 0; b < B; ++b)
+      if (rp[b]->n) {
+        shift_points_kernel<<<ceil_div(rp[b]->n, 256), 256, 0, s>>>(rp[b]->feat.p, (int)rp[b]->n, shift.p + 4 * b);
+        ctx_count_launches(ctx, 1);
+      }
+    apply_filters(ctx, cfg_.reference_filters, rp);
+  } else {
+    // ICP::compute: reference filters, THEN mean-centre (§3.3)
+    apply_filters(ctx, cfg_.reference_filters, rp);
+    compute_mean();
+  }
+  std::vector<const float4*> pts(B);
+  std::vector<int> ns(B);
+  for (int b = 0; b < B; ++b) { pts[b] = rp[b]->feat.p; ns[b] = (int)rp[b]->n; }
+  std::vector<std::unique_ptr<Index>> idx;
+  build_indices(ctx, pts, ns, centre_first ? nullptr : shift.p, idx);
+  std::vector<double> hT((size_t)16 * B);
+  Tmean.download(hT.data(), hT.size());
+  out.clear();
+  for (int b = 0; b < B; ++b) {
+    auto pr = std::make_unique<PreparedRef>();
+    pr->index = std::move(idx[b]);
+    const Desc* nrm = rp[b]->find("normals");
+    pr->has_normals = nrm != nullptr;
+    if (nrm && ns[b] > 0) {
+      pr->normals_sorted.reset(ctx, (size_t)ns[b]);
+      gather_vec3_sorted_kernel<<<ceil_div(ns[b], 256), 256, 0, s>>>(pr->index->pts.p, ns[b], nrm->data.p, 3,
+                                                                    pr->normals_sorted.p, nullptr);
+      ctx_count_launches(ctx, 1);
+    }
+    pr->cloud = std::move(refs[b]);
+    out.push_back(std::move(pr));
+  }
+  ctx->sync();  // Tmean on the host (one sync per prepare, not per iteration)
+  for (int b = 0; b < B; ++b) std::memcpy(out[b]->T_refIn_refMean, hT.data() + 16 * b, 16 * sizeof(double));
+  PGS_LAUNCH_CHECK();
+}
+
+void IcpEngine::run_batch(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
+                          const double* T_inits, pgs_icp_result* results) {
+  const int P = (int)readings.size();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx_->profiling) {
+    PGS_CUDA(cudaEventCreate(&e0));
+    PGS_CUDA(cudaEventCreate(&e1));
+    PGS_CUDA(cudaEventRecord(e0, ctx_->stream));
+  }
+  std::vector<std::unique_ptr<Cloud>> refs(P);
+  for (int p = 0; p < P; ++p) refs[p] = references[p]->clone();
+  std::vector<std::unique_ptr<PreparedRef>> prepared;
+  prepare_references(refs, false, prepared);
+  if (ctx_->profiling) {
+    PGS_CUDA(cudaEventRecord(e1, ctx_->stream));
+    PGS_CUDA(cudaEventSynchronize(e1));
+    PGS_CUDA(cudaEventElapsedTime(&ctx_->times.index_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  std::vector<const PreparedRef*> rp(P);
+  for (int p = 0; p < P; ++p) rp[p] = prepared[p].get();
+  run_prepared(readings, rp, T_inits, results);
+}
+
+void IcpEngine::set_map(const Cloud& map) {
+  if (map.n == 0) throw Error(PGS_CONVERGENCE_ERROR, "ICPSequence::setMap: empty map");
+  std::vector<std::unique_ptr<Cloud>> refs(1);
+  refs[0] = map.clone();
+  std::vector<std::unique_ptr<PreparedRef>> prepared;
+  prepare_references(refs, true, prepared);
+  map_ = std::move(prepared[0]);
+}
+
+void IcpEngine::run_sequence(const Cloud& reading, const double* T_init, pgs_icp_result* out) {
+  if (!map_) throw Error(PGS_INVALID_FIELD, "ICPSequence: no map set (call setMap first)");
+  std::vector<const Cloud*> rd{&reading};
+  std::vector<const PreparedRef*> rp{map_.get()};
+  run_prepared(rd, rp, T_init, out);
+}
+
+void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const std::vector<const PreparedRef*>& refs,
+                             const double* T_inits, pgs_icp_result* results) {
+  Ctx* ctx = ctx_;
+  cudaStream_t s = ctx->stream;
+  const int P = (int)readings.size();
+  const IcpParams& prm = params_;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (ctx->profiling) {
+    for (auto& e : ev) PGS_CUDA(cudaEventCreate(&e));
+    PGS_CUDA(cudaEventRecord(ev[0], s));
+  }
+
+  // ---- reading side: copy, reading filters ---------------------------------
+  std::vector<std::unique_ptr<Cloud>> rds(P);
+  std::vector<Cloud*> rdp(P);
+  for (int p = 0; p < P; ++p) { rds[p] = readings[p]->clone(); rdp[p] = rds[p].get(); }
+  apply_filters(ctx, cfg_.reading_filters, rdp);
+
+  // ---- initial state ---------------------------------------------------------
+  std::vector<PairState> hs(P);
+  std::vector<double> hTm((size_t)16 * P);
+  int n_active = 0;
+  for (int p = 0; p < P; ++p) {
+    PairState& st = hs[p];
+    std::memset(&st, 0, sizeof(st));
+    if (T_inits) std::memcpy(st.T_init, T_inits + 16 * p, 16 * sizeof(double));
+    else { st.T_init[0] = st.T_init[5] = st.T_init[10] = st.T_init[15] = 1.0; }
+    std::memcpy(hTm.data() + 16 * p, refs[p]->T_refIn_refMean, 16 * sizeof(double));
+    st.status = PGS_OK;
+    if (!is_rigid(st.T_init)) st.status = PGS_TRANSFORMATION_ERROR;
+    else if (prm.minimizer != MIN_P2POINT && !refs[p]->has_normals) st.status = PGS_INVALID_FIELD;
+    else if (rdp[p]->n == 0 || refs[p]->index->n == 0) st.status = PGS_CONVERGENCE_ERROR;
+    st.active = st.status == PGS_OK;
+    if (st.status == PGS_TRANSFORMATION_ERROR) {  // keep the pose algebra finite
+      std::memset(st.T_init, 0, sizeof(st.T_init));
+      st.T_init[0] = st.T_init[5] = st.T_init[10] = st.T_init[15] = 1.0;
+    }
+    n_active += st.active;
+  }
+  DBuf<PairState> d_states(ctx, P);
+  DBuf<double> d_Tm(ctx, (size_t)16 * P);
+  ctx->upload_small(d_states.p, hs.data(), sizeof(PairState) * P);
+  ctx->upload_small(d_Tm.p, hTm.data(), sizeof(double) * 16 * P);
+  init_state_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, d_Tm.p, P);
+  ctx_count_launches(ctx, 1);
+
+  // ---- transformations.apply(reading, T_refMean_dataIn), Morton order --------
+  int max_nr = 0;
+  {
+    std::vector<PreJob> pj(P);
+    for (int p = 0; p < P; ++p) {
+      Desc* nrm = rdp[p]->find("normals");
+      Desc* obs = rdp[p]->find("observationDirections");
+      pj[p] = PreJob{rdp[p]->feat.p, nrm ? nrm->data.p : nullptr, obs ? obs->data.p : nullptr, (int)rdp[p]->n};
+      max_nr = std::max(max_nr, (int)rdp[p]->n);
+    }
+    if (max_nr > 0) {
+      DBuf<PreJob> d_pj(ctx, P);
+      ctx->upload_small(d_pj.p, pj.data(), sizeof(PreJob) * P);
+      pretransform_kernel<<<dim3(ceil_div(max_nr, 256), P), 256, 0, s>>>(d_pj.p, d_states.p);
+      ctx_count_launches(ctx, 1);
+    }
+  }
+  std::vector<std::unique_ptr<Index>> rd_sorted;
+  {
+    std::vector<const float4*> pts(P);
+    std::vector<int> ns(P);
+    for (int p = 0; p < P; ++p) { pts[p] = rdp[p]->feat.p; ns[p] = (int)rdp[p]->n; }
+    build_indices(ctx, pts, ns, nullptr, rd_sorted);
+  }
+
+  // ---- per-pair views ----------------------------------------------------------
+  const int acc_blocks = std::max(1, std::min(ceil_div(max_nr, 1024), ctx->num_sms));
+  std::vector<PairView> hv(P);
+  std::vector<DBuf<int>> mpos(P);
+  std::vector<DBuf<float>> md2(P);
+  std::vector<DBuf<double>> partials(P);
+  std::vector<DBuf<float4>> rdn(P);
+  std::vector<DBuf<float>> rdnoise(P);
+  for (int p = 0; p < P; ++p) {
+    const int nr = (int)rdp[p]->n;
+    mpos[p].reset(ctx, (size_t)std::max(nr, 1));
+    md2[p].reset(ctx, (size_t)std::max(nr, 1));
+    partials[p].reset(ctx, (size_t)acc_blocks * kAcc2);
+    PairView v;
+    std::memset(&v, 0, sizeof(v));
+    v.reading = rd_sorted[p]->pts.p;
+    v.n_r = nr;
+    v.tree = refs[p]->index->view();
+    v.ref_normals = refs[p]->has_normals ? refs[p]->normals_sorted.p : nullptr;
+    const Desc* nrm = rdp[p]->find("normals");
+    const Desc* noise = rdp[p]->find("simpleSensorNoise");
+    if (nrm && noise && nr > 0 && prm.minimizer != MIN_P2POINT) {
+      rdn[p].reset(ctx, (size_t)nr);
+      rdnoise[p].reset(ctx, (size_t)nr);
+      gather_vec3_sorted_kernel<<<ceil_div(nr, 256), 256, 0, s>>>(rd_sorted[p]->pts.p, nr, nrm->data.p, 3, rdn[p].p, nullptr);
+      gather_vec3_sorted_kernel<<<ceil_div(nr, 256), 256, 0, s>>>(rd_sorted[p]->pts.p, nr, noise->data.p, 1, nullptr, rdnoise[p].p);
+      ctx_count_launches(ctx, 2);
+      v.rd_normals = rdn[p].p;
+      v.rd_noise = rdnoise[p].p;
+    }
+    v.match_pos = mpos[p].p;
+    v.match_d2 = md2[p].p;
+    v.partials = partials[p].p;
+    hv[p] = v;
+  }
+  DBuf<PairView> d_views(ctx, P);
+  ctx->upload_small(d_views.p, hv.data(), sizeof(PairView) * P);
+
+  // ---- the loop ------------------------------------------------------------------
+  ctx->ensure_progress();
+  DBuf<int> d_nactive(ctx, 1);
+  ctx->upload_small(d_nactive.p, &n_active, sizeof(int));
+  *ctx->h_progress = (n_active == 0) ? 1 : 0;
+  if (ctx->profiling) PGS_CUDA(cudaEventRecord(ev[1], s));
+  int launched = 0;
+  const int max_it = prm.hard_iteration_cap;
+  const dim3 gm(ceil_div(std::max(max_nr, 1), 128), P), ga(acc_blocks, P);
+  for (int it = 0; it < max_it; ++it) {
+    if (*ctx->h_progress) break;
+    if (it >= 2) {
+      // stay at most two iterations ahead of the device, then look at the flag
+      PGS_CUDA(cudaEventSynchronize(ctx->loop_ev[it & 1]));
+      if (*ctx->h_progress) break;
+    }
+    match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+    if (prm.n_quant > 0) select_kernel<<<P, 1024, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    ctx_count_launches(ctx, prm.n_quant > 0 ? 3 : 2);
+    PGS_CUDA(cudaEventRecord(ctx->loop_ev[it & 1], s));
+    ++launched;
+  }
+  if (ctx->profiling) PGS_CUDA(cudaEventRecord(ev[2], s));
+
+  // ---- covariance / overlap / final pose -------------------------------------------
+  bool need_final = prm.minimizer == MIN_P2PLANE_COV;
+  for (int p = 0; p < P; ++p) need_final = need_final || hv[p].rd_normals != nullptr;
+  if (need_final) {
+    final_accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm);
+    ctx_count_launches(ctx, 1);
+  }
+  finish_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_views.p, d_states.p, prm, P);
+  ctx_count_launches(ctx, 1);
+  PGS_LAUNCH_CHECK();
+  d_states.download(hs.data(), P);
+  if (ctx->profiling) PGS_CUDA(cudaEventRecord(ev[3], s));
+  ctx->sync();
+  for (int p = 0; p < P; ++p) {
+    const PairState& st = hs[p];
+    pgs_icp_result& r = results[p];
+    std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.T, st.T_out, sizeof(r.T));
+    std::memcpy(r.covariance, st.cov, sizeof(r.covariance));
+    r.iterations = st.iterations;
+    r.max_iterations_reached = st.max_reached;
+    r.status = st.status;
+    r.n_reading = rdp[p]->n;
+    r.n_reference = refs[p]->index->n;
+    if (st.status == PGS_OK && st.iterations > 0 && rdp[p]->n > 0) {
+      r.overlap = st.overlap;
+      r.weighted_point_used_ratio = st.wsum / (double)rdp[p]->n;
+      r.point_used_ratio = st.kept / (double)rdp[p]->n;
+      r.residual = st.resid;
+    }
+  }
+  if (ctx->profiling) {
+    pgs_stage_times& t = ctx->times;
+    PGS_CUDA(cudaEventElapsedTime(&t.filters_ms, ev[0], ev[1]));
+    PGS_CUDA(cudaEventElapsedTime(&t.loop_ms, ev[1], ev[2]));
+    PGS_CUDA(cudaEventElapsedTime(&t.total_ms, ev[0], ev[3]));
+    t.iterations_launched = launched;
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fine-grained modules
+// ---------------------------------------------------------------------------
+void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const float* d_d2, int64_t nk, float* d_w) {
+  IcpParams p;
+  std::memset(&p, 0, sizeof(p));
+  outlier_limits_params(filters, &p);
+  float hi = p.fixed_hi, lo = p.fixed_lo;
+  if (p.n_quant > 0) {
+    DBuf<float> q(ctx, kMaxQuant);
+    DBuf<int> fail(ctx, kMaxQuant);
+    for (int j = 0; j < p.n_quant; ++j) {
+      quantile_kernel<<<1, 1024, 0, ctx->stream>>>(d_d2, nk, p.q_ratio[j], q.p + j, fail.p + j);
+      ctx_count_launches(ctx, 1);
+    }
+    float hq[kMaxQuant];
+    int hf[kMaxQuant];
+    q.download(hq, p.n_quant);
+    fail.download(hf, p.n_quant);
+    ctx->sync();
+    for (int j = 0; j < p.n_quant; ++j) {
+      if (hf[j]) throw Error(PGS_CONVERGENCE_ERROR, "no outlier to filter");
+      volatile float lim = p.q_factor[j] * hq[j];
+      hi = std::min(hi, (float)lim);
+    }
+  }
+  if (nk > 0) {
+    weights_kernel<<<ceil_div(nk, 256), 256, 0, ctx->stream>>>(d_d2, nk, p.has_outliers, lo, hi, d_w);
+    ctx_count_launches(ctx, 1);
+  }
+  PGS_LAUNCH_CHECK();
+}
+
+void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, const Cloud& reference,
+                     const int32_t* d_ids, const float* d_d2, const float* d_w, int k, pgs_min_result* out) {
+  ChainConfig tmp;
+  int mz;
+  if (minimizer.name == "PointToPlaneErrorMinimizer") mz = MIN_P2PLANE;
+  else if (minimizer.name == "PointToPlaneWithCovErrorMinimizer") mz = MIN_P2PLANE_COV;
+  else if (minimizer.name == "PointToPointErrorMinimizer") mz = MIN_P2POINT;
+  else throw Error(PGS_INVALID_ELEMENT, "ErrorMinimizer " + minimizer.name + " has no device implementation");
+  const Desc* rn = reference.find("normals");
+  if (mz != MIN_P2POINT && !rn) throw Error(PGS_INVALID_FIELD, "Cannot find descriptor normals in the reference cloud");
+  const Desc* rdn = reading.find("normals");
+  const Desc* rdz = reading.find("simpleSensorNoise");
+  std::memset(out, 0, sizeof(*out));
+  out->T[0] = out->T[5] = out->T[10] = out->T[15] = 1.0;
+  const int64_t total = reading.n * k;
+  const int nb = std::max(1, std::min(ceil_div(total, 1024), ctx->num_sms));
+  DBuf<double> partials(ctx, (size_t)nb * kAcc2);
+  ExplicitJob job{reading.feat.p, reference.feat.p, rn ? rn->data.p : nullptr, rdn ? rdn->data.p : nullptr,
+                  rdz ? rdz->data.p : nullptr, d_ids, d_d2, d_w, reading.n, k, partials.p};
+  std::vector<double> hp((size_t)nb * kAcc2);
+  auto reduce = [&](double* acc) {
+    partials.download(hp.data(), hp.size());
+    ctx->sync();
+    for (int j = 0; j < kAcc2; ++j) {
+      double s = 0.0;
+      for (int b = 0; b < nb; ++b) s += hp[(size_t)b * kAcc2 + j];
+      acc[j] = s;
+    }
+  };
+  explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 0, 0, 0, 0, 0, 0, 0);
+  ctx_count_launches(ctx, 1);
+  PGS_LAUNCH_CHECK();
+  double acc[kAcc2];
+  reduce(acc);
+  if (!(acc[28] > 0.0)) throw Error(PGS_CONVERGENCE_ERROR, "no point to minimize");
+  out->kept = (int64_t)acc[28];
+  out->point_used_ratio = acc[28] / (double)total;
+  out->weighted_point_used_ratio = acc[29] / (double)total;
+  out->residual = acc[27];
+  // the 6x6 / 3x3 solve of this module-level call runs on the device too, in
+  // the same single-thread routine the fused loop uses
+  DBuf<PairState> st(ctx, 1);
+  PairState hs;
+  std::memset(&hs, 0, sizeof(hs));
+  hs.T_init[0] = hs.T_init[5] = hs.T_init[10] = hs.T_init[15] = 1.0;
+  hs.active = 1;
+  ctx->upload_small(st.p, &hs, sizeof(hs));
+  DBuf<double> Tm(ctx, 16);
+  double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  ctx->upload_small(Tm.p, I, sizeof(I));
+  init_state_kernel<<<1, 32, 0, ctx->stream>>>(st.p, Tm.p, 1);
+  DBuf<double> d_acc(ctx, kAcc2);
+  ctx->upload_small(d_acc.p, acc, sizeof(double) * kAcc2);
+  IcpParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.minimizer = mz;
+  prm.hard_iteration_cap = 1 << 30;
+  prm.sensor_std_dev = mz == MIN_P2PLANE_COV ? minimizer.real("sensorStdDev") : 0.01;
+  ctx->ensure_progress();
+  DBuf<int> na(ctx, 1);
+  int one = 1 << 20;
+  ctx->upload_small(na.p, &one, sizeof(int));
+  solve_only_kernel_launch(ctx, st.p, d_acc.p, prm, na.p);
+  st.download(&hs, 1);
+  ctx->sync();
+  if (hs.status != PGS_OK && hs.status != PGS_TRANSFORMATION_ERROR) throw Error(hs.status, "error minimizer failed");
+  std::memcpy(out->T, hs.T_inc, sizeof(out->T));
+  const bool want_overlap = rdn && rdz && mz != MIN_P2POINT;
+  out->overlap = out->weighted_point_used_ratio;
+  if (mz == MIN_P2PLANE_COV || want_overlap) {
+    const double* Ti = hs.T_inc;
+    double beta = -std::asin(Ti[2]);
+    double alpha = std::atan2(Ti[6], Ti[10]);
+    double cb = std::cos(beta);
+    double gamma = std::atan2(Ti[1] / cb, Ti[0] / cb);
+    explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 1, alpha, beta, gamma, Ti[12], Ti[13], Ti[14]);
+    ctx_count_launches(ctx, 1);
+    PGS_LAUNCH_CHECK();
+    double acc2[kAcc2];
+    reduce(acc2);
+    if (want_overlap) out->overlap = acc2[43] > 0.0 ? acc2[42] / acc2[43] : 0.0;
+    if (mz == MIN_P2PLANE_COV) {
+      std::memcpy(hs.acc2, acc2, sizeof(acc2));
+      hs.wsum = acc[29];
+      hs.iterations = 1;
+      hs.status = PGS_OK;
+      ctx->upload_small(st.p, &hs, sizeof(hs));
+      PairView v;
+      std::memset(&v, 0, sizeof(v));
+      v.n_r = (int)reading.n;
+      DBuf<PairView> dv(ctx, 1);
+      ctx->upload_small(dv.p, &v, sizeof(v));
+      finish_kernel<<<1, 32, 0, ctx->stream>>>(dv.p, st.p, prm, 1);
+      ctx_count_launches(ctx, 1);
+      st.download(&hs, 1);
+      ctx->sync();
+      std::memcpy(out->covariance, hs.cov, sizeof(out->covariance));
+    }
+  }
+}
+
+}  // namespace pgs

@@ -1,0 +1,210 @@
+// index.cu — the spatial index that replaces libnabo's kd-tree
+// (KDTreeMatcher::init -> NNS::create).
+//
+// B200 shape instead of a pointer-built unbalanced kd-tree: points are sorted
+// by 30-bit Morton code on the device, cut into leaves of kLeaf consecutive
+// points (one 128-byte line of float4 each), and covered by an implicit
+// complete binary tree of axis-aligned boxes.  No child pointers: node i has
+// children 2i and 2i+1, stored adjacently (48 bytes = three float4 loads), and
+// traversal needs no stack (see knn.cu).  Exactness of the search does not
+// depend on the tree shape, only on the boxes being conservative, so parity
+// with the reference's kd-tree is parity of RESULTS (exact (dist, index)
+// minima), not of visit order.
+#include "core.cuh"
+
+namespace pgs {
+
+namespace {
+
+struct BuildJob {
+  const float4* src;
+  float4* dst;    // sorted points (n_leaves * kLeaf entries)
+  float* nodes;   // 2*P*6 floats
+  int n, n_leaves, P, depth;
+};
+
+__global__ void bbox_init_kernel(unsigned* bbox, int n_jobs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_jobs * 6) bbox[i] = (i % 6 < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+bbox_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift, unsigned* __restrict__ bbox) {
+  const BuildJob job = jobs[blockIdx.y];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (shift) { sx = shift[4 * blockIdx.y]; sy = shift[4 * blockIdx.y + 1]; sz = shift[4 * blockIdx.y + 2]; }
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x) {
+    float4 p = job.src[i];
+    unsigned ux = f2ord(__fsub_rn(p.x, sx)), uy = f2ord(__fsub_rn(p.y, sy)), uz = f2ord(__fsub_rn(p.z, sz));
+    lo[0] = min(lo[0], ux); hi[0] = max(hi[0], ux);
+    lo[1] = min(lo[1], uy); hi[1] = max(hi[1], uy);
+    lo[2] = min(lo[2], uz); hi[2] = max(hi[2], uz);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+    hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned* bb = bbox + 6 * blockIdx.y;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(bb + d, lo[d]);
+      atomicMax(bb + 3 + d, hi[d]);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+morton_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift,
+              const unsigned* __restrict__ bbox, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+              int stride) {
+  const BuildJob job = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= job.n) return;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (shift) { sx = shift[4 * blockIdx.y]; sy = shift[4 * blockIdx.y + 1]; sz = shift[4 * blockIdx.y + 2]; }
+  const unsigned* bb = bbox + 6 * blockIdx.y;
+  float lo[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])};
+  float hi[3] = {ord2f(bb[3]), ord2f(bb[4]), ord2f(bb[5])};
+  float4 p = job.src[i];
+  float c[3] = {__fsub_rn(p.x, sx), __fsub_rn(p.y, sy), __fsub_rn(p.z, sz)};
+  // one cubic grid over the longest extent keeps cells isotropic
+  float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+  float scale = ext > 0.f ? 1023.0f / ext : 0.f;
+  unsigned q[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float f = (c[d] - lo[d]) * scale;
+    int v = (int)f;
+    q[d] = (unsigned)max(0, min(1023, v));
+  }
+  keys[(size_t)blockIdx.y * stride + i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+  vals[(size_t)blockIdx.y * stride + i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+gather_sorted_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift,
+                     const uint32_t* __restrict__ vals, int stride) {
+  const BuildJob job = jobs[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= job.n_leaves * kLeaf) return;
+  float4 o;
+  if (j < job.n) {
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (shift) { sx = shift[4 * blockIdx.y]; sy = shift[4 * blockIdx.y + 1]; sz = shift[4 * blockIdx.y + 2]; }
+    uint32_t src = vals[(size_t)blockIdx.y * stride + j];
+    float4 p = job.src[src];
+    o = make_float4(__fsub_rn(p.x, sx), __fsub_rn(p.y, sy), __fsub_rn(p.z, sz), __int_as_float((int)src));
+  } else {
+    // padding: +inf coordinates give dist = +inf, index INT_MAX never wins a tie
+    const float inf = __int_as_float(0x7f800000);
+    o = make_float4(inf, inf, inf, __int_as_float(0x7fffffff));
+  }
+  job.dst[j] = o;
+}
+
+__global__ void __launch_bounds__(256) leaf_box_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildJob job = jobs[blockIdx.y];
+  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= job.P) return;
+  const float inf = __int_as_float(0x7f800000);
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  if (leaf < job.n_leaves) {
+    const float4* lp = job.dst + (size_t)leaf * kLeaf;
+#pragma unroll
+    for (int j = 0; j < kLeaf; ++j) {
+      if (leaf * kLeaf + j < job.n) {
+        float4 p = lp[j];
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+      }
+    }
+  }
+  float* nd = job.nodes + (size_t)(job.P + leaf) * 6;
+  nd[0] = lo[0]; nd[1] = lo[1]; nd[2] = lo[2];
+  nd[3] = hi[0]; nd[4] = hi[1]; nd[5] = hi[2];
+}
+
+// one block per job walks the levels bottom-up
+__global__ void __launch_bounds__(1024) upper_levels_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildJob job = jobs[blockIdx.x];
+  for (int width = job.P >> 1; width >= 1; width >>= 1) {
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+      const int node = width + i;
+      const float* a = job.nodes + (size_t)(2 * node) * 6;
+      float* o = job.nodes + (size_t)node * 6;
+      o[0] = fminf(a[0], a[6]); o[1] = fminf(a[1], a[7]); o[2] = fminf(a[2], a[8]);
+      o[3] = fmaxf(a[3], a[9]); o[4] = fmaxf(a[4], a[10]); o[5] = fmaxf(a[5], a[11]);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std::vector<int>& n,
+                   const float* d_shift, std::vector<std::unique_ptr<Index>>& out) {
+  const int B = (int)d_pts.size();
+  out.clear();
+  if (B == 0) return;
+  int max_n = 0;
+  std::vector<BuildJob> jobs(B);
+  for (int b = 0; b < B; ++b) {
+    auto idx = std::make_unique<Index>();
+    idx->ctx = ctx;
+    idx->n = n[b];
+    idx->n_leaves = ceil_div(n[b] > 0 ? n[b] : 1, kLeaf);
+    idx->P = next_pow2(idx->n_leaves);
+    idx->depth = 0;
+    while ((1 << idx->depth) < idx->P) ++idx->depth;
+    idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
+    idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
+    jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->n, idx->n_leaves, idx->P, idx->depth};
+    if (n[b] > max_n) max_n = n[b];
+    out.push_back(std::move(idx));
+  }
+  const int stride = ceil_div(max_n > 0 ? max_n : 1, kSortChunk) * kSortChunk;
+  DBuf<BuildJob> d_jobs(ctx, B);
+  ctx->upload_small(d_jobs.p, jobs.data(), sizeof(BuildJob) * B);
+  DBuf<int> d_n(ctx, B);
+  ctx->upload_small(d_n.p, n.data(), sizeof(int) * B);
+  DBuf<unsigned> bbox(ctx, (size_t)6 * B);
+  DBuf<uint32_t> ka(ctx, (size_t)B * stride), kb(ctx, (size_t)B * stride), va(ctx, (size_t)B * stride),
+      vb(ctx, (size_t)B * stride);
+  cudaStream_t s = ctx->stream;
+  bbox_init_kernel<<<ceil_div(6 * B, 256), 256, 0, s>>>(bbox.p, B);
+  if (max_n > 0) {
+    int nb = std::min(ceil_div(max_n, 256 * 4), 64);
+    bbox_kernel<<<dim3(nb, B), 256, 0, s>>>(d_jobs.p, d_shift, bbox.p);
+    morton_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, s>>>(d_jobs.p, d_shift, bbox.p, ka.p, va.p, stride);
+    ctx_count_launches(ctx, 2);
+  }
+  bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_n.p, B, stride, max_n, 30);
+  const uint32_t* sorted_vals = in_b ? vb.p : va.p;
+  int max_leaves = 0, max_P = 0;
+  for (int b = 0; b < B; ++b) {
+    max_leaves = std::max(max_leaves, out[b]->n_leaves);
+    max_P = std::max(max_P, out[b]->P);
+  }
+  gather_sorted_kernel<<<dim3(ceil_div(max_leaves * kLeaf, 256), B), 256, 0, s>>>(d_jobs.p, d_shift, sorted_vals, stride);
+  leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
+  upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
+  ctx_count_launches(ctx, 4);
+  PGS_LAUNCH_CHECK();
+  // job tables went through the pinned ring; device temporaries are
+  // stream-ordered, so no sync is needed here.
+}
+
+}  // namespace pgs

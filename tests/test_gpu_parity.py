@@ -1,0 +1,443 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs.  Bit-exact for ids / distances / weights / filter outputs;
+poses within 1e-5 m and 1e-5 rad with equal iteration counts (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from pgslam_b200 import synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pm(ctx):
+    from pgslam_b200 import pm as _pm
+    _pm._DEFAULT_CTX = ctx
+    return _pm
+
+
+@pytest.fixture(scope="module")
+def pair30k():
+    return synth.scan_pair(3, beams=16, az_steps=1875)
+
+
+@pytest.fixture(scope="module")
+def pair120k():
+    return synth.scan_pair(5, beams=64, az_steps=1875)
+
+
+# ---------------------------------------------------------------- kNN (A9) ---
+@pytest.mark.parametrize("k", [1, 5, 10, 32])
+def test_knn_bit_exact_30k(pm, pair30k, k):
+    rd, rf, _ = pair30k
+    m = pm.Matcher("KDTreeMatcher", {"knn": k})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd))
+    ids, d2 = ob.kdtree_knn(rf, rd, k=k)
+    assert np.array_equal(got.ids, ids)
+    assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+
+
+def test_knn_bit_exact_120k(pm, pair120k):
+    rd, rf, _ = pair120k
+    m = pm.Matcher("KDTreeMatcher", {"knn": 1})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd))
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    assert np.array_equal(got.ids, ids)
+    assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+
+
+def test_knn_ties_lower_index_and_max_dist(pm):
+    g = np.random.default_rng(0)
+    base = g.uniform(-5, 5, size=(3, 500)).astype(np.float32)
+    ref = np.ones((4, 1500), np.float32)
+    ref[:3] = np.concatenate([base, base, base], axis=1)  # every point three times -> exact ties
+    q = np.ones((4, 300), np.float32)
+    q[:3] = g.uniform(-5, 5, size=(3, 300)).astype(np.float32)
+    for k, md in ((1, np.inf), (4, np.inf), (3, 0.7)):
+        m = pm.Matcher("KDTreeMatcher", {"knn": k, "maxDist": md})
+        m.init(pm.DataPoints(ref))
+        got = m.findClosests(pm.DataPoints(q))
+        ids, d2 = ob.brute_knn(ref, q, k=k, max_dist=md)
+        assert np.array_equal(got.ids, ids)
+        assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+    if True:
+        m = pm.Matcher("KDTreeMatcher", {"knn": 1})
+        m.init(pm.DataPoints(ref))
+        got = m.findClosests(pm.DataPoints(q))
+        assert (got.ids < 500).all()  # lower index of each triple wins
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 63, 513])
+def test_knn_small_and_ragged(pm, n):
+    g = np.random.default_rng(n)
+    ref = np.ones((4, n), np.float32)
+    ref[:3] = g.normal(size=(3, n)).astype(np.float32)
+    q = np.ones((4, 37), np.float32)
+    q[:3] = g.normal(size=(3, 37)).astype(np.float32)
+    k = min(3, n)
+    m = pm.Matcher("KDTreeMatcher", {"knn": k})
+    m.init(pm.DataPoints(ref))
+    got = m.findClosests(pm.DataPoints(q))
+    ids, d2 = ob.brute_knn(ref, q, k=k)
+    assert np.array_equal(got.ids, ids)
+    assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+
+
+def test_knn_more_neighbours_than_points(pm):
+    ref = np.ones((4, 2), np.float32)
+    ref[:3, 0] = (0, 0, 0)
+    ref[:3, 1] = (1, 0, 0)
+    q = np.ones((4, 1), np.float32)
+    q[:3, 0] = (0.1, 0, 0)
+    m = pm.Matcher("KDTreeMatcher", {"knn": 4})
+    m.init(pm.DataPoints(ref))
+    got = m.findClosests(pm.DataPoints(q))
+    assert got.ids[:, 0].tolist() == [0, 1, -1, -1]
+    assert np.isinf(got.dists[2:, 0]).all()
+
+
+# ------------------------------------------------------------ filters (A3-A7) ---
+def _cmp_cloud(dp, oc, exact=True):
+    assert dp.getNbPoints() == oc.n
+    assert np.array_equal(dp.features.view(np.uint32), oc.features.view(np.uint32))
+    want = oc.descriptors()
+    got = dp.descriptors
+    assert set(got) == set(want)
+    for lab in want:
+        if exact:
+            assert np.array_equal(got[lab].view(np.uint32), want[lab].view(np.uint32)), lab
+        else:
+            np.testing.assert_allclose(got[lab], want[lab], rtol=1e-6, atol=1e-7, err_msg=lab)
+
+
+def test_surface_normal_filter_bit_exact(pm, pair30k):
+    _, rf, _ = pair30k
+    params = {"knn": 10, "keepNormals": 1, "keepDensities": 1, "keepEigenValues": 1, "keepEigenVectors": 1}
+    dp = pm.DataPoints(rf)
+    f = pm.DataPointsFilters()
+    f.append("SurfaceNormalDataPointsFilter", params)
+    f.apply(dp)
+    oc = ob.Cloud(rf)
+    assert ob.apply_filter(oc, "SurfaceNormalDataPointsFilter", **params) == 0
+    _cmp_cloud(dp, oc)
+
+
+def test_input_filter_chain_bit_exact(pm, pair30k):
+    rd, _, _ = pair30k
+    dp = pm.DataPoints(rd)
+    pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS)).apply(dp)
+    oc = ob.Cloud(rd)
+    for it in util.INPUT_FILTERS:
+        (name, p), = ob._modlist([it])
+        assert ob.apply_filter(oc, name, **p) == 0
+    _cmp_cloud(dp, oc)
+    assert {l for l, _ in dp.descriptorLabels()} == {"normals", "observationDirections", "simpleSensorNoise"}
+
+
+@pytest.mark.parametrize("centroid", [1, 0])
+def test_voxel_grid_bit_exact(pm, pair120k, centroid):
+    rd, _, _ = pair120k
+    params = {"vSizeX": 0.2, "vSizeY": 0.25, "vSizeZ": 0.2, "useCentroid": centroid, "averageExistingDescriptors": 1}
+    dp = pm.DataPoints(rd, {"simpleSensorNoise": np.linspace(0, 1, rd.shape[1], dtype=np.float32)[None]})
+    f = pm.DataPointsFilters()
+    f.append("VoxelGridDataPointsFilter", params)
+    f.apply(dp)
+    oc = ob.Cloud(rd, {"simpleSensorNoise": np.linspace(0, 1, rd.shape[1], dtype=np.float32)[None]})
+    assert ob.apply_filter(oc, "VoxelGridDataPointsFilter", **params) == 0
+    assert 1000 < oc.n < rd.shape[1]
+    _cmp_cloud(dp, oc)
+
+
+@pytest.mark.parametrize("name,params", [
+    ("RandomSamplingDataPointsFilter", {"prob": 0.6, "seed": 7}),
+    ("MaxDistDataPointsFilter", {"dim": -1, "maxDist": 20.0}),
+    ("MinDistDataPointsFilter", {"dim": 0, "minDist": 1.5}),
+])
+def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
+    rd, _, _ = pair30k
+    dp = pm.DataPoints(rd)
+    f = pm.DataPointsFilters()
+    f.append(name, params)
+    f.apply(dp)
+    oc = ob.Cloud(rd)
+    assert ob.apply_filter(oc, name, **params) == 0
+    assert 0 < oc.n < rd.shape[1]
+    _cmp_cloud(dp, oc)
+
+
+def test_rigid_transformation_bit_exact_and_rigidity_check(pm, pair30k):
+    rd, _, truth = pair30k
+    dp = pm.DataPoints(rd)
+    pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS[:2])).apply(dp)
+    out = pm.RigidTransformation().compute(dp, truth)
+    oc = ob.Cloud(rd)
+    for it in util.INPUT_FILTERS[:2]:
+        (name, p), = ob._modlist([it])
+        ob.apply_filter(oc, name, **p)
+    assert ob.rigid_transform(oc, truth) == 0
+    _cmp_cloud(out, oc)
+    bad = truth.copy()
+    bad[:3, :3] *= 1.1
+    with pytest.raises(pm.TransformationError):
+        pm.RigidTransformation().compute(dp, bad)
+
+
+def test_concatenate_keeps_common_descriptors(pm, pair30k):
+    rd, rf, _ = pair30k
+    a = pm.DataPoints(rd[:, :1000], {"normals": np.zeros((3, 1000), np.float32), "densities": np.ones((1, 1000), np.float32)})
+    b = pm.DataPoints(rf[:, :500], {"normals": np.ones((3, 500), np.float32)})
+    a.concatenate(b)
+    assert a.getNbPoints() == 1500
+    assert [l for l, _ in a.descriptorLabels()] == ["normals"]
+    assert np.array_equal(a.features[:, 1000:], rf[:, :500])
+    assert a.getDescriptorByName("normals")[:, 1000:].min() == 1.0
+
+
+# ------------------------------------------------- outliers + minimizers (A10-A13) ---
+@pytest.mark.parametrize("filters", [
+    [{"TrimmedDistOutlierFilter": {"ratio": 0.85}}],
+    [{"TrimmedDistOutlierFilter": {"ratio": 1.0}}],
+    [{"MedianDistOutlierFilter": {"factor": 3}}, {"MaxDistOutlierFilter": {"maxDist": 0.5}}],
+    [{"MinDistOutlierFilter": {"minDist": 0.01}}, {"TrimmedDistOutlierFilter": {"ratio": 0.5}}],
+    [],
+])
+def test_outlier_weights_bit_exact(pm, pair30k, filters):
+    rd, rf, _ = pair30k
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    d2 = d2.copy()
+    d2[0, :50] = 0.0       # exact hits are excluded from the quantile (A.3)
+    d2[0, 50:60] = np.inf  # unfound matches
+    o = pm.OutlierFilters()
+    for it in filters:
+        (name, p), = ob._modlist([it])
+        o.append(name, p)
+    got = o.compute(pm.DataPoints(rd), pm.DataPoints(rf), pm.Matches(ids, d2))
+    st, want = ob.outlier_weights(filters, d2)
+    assert st == 0
+    assert np.array_equal(got, want)
+
+
+def test_outlier_no_valid_distance_is_convergence_error(pm):
+    q = np.ones((4, 10), np.float32)
+    d2 = np.zeros((1, 10), np.float32)
+    o = pm.OutlierFilters()
+    o.append("TrimmedDistOutlierFilter", {"ratio": 0.85})
+    with pytest.raises(pm.ConvergenceError):
+        o.compute(pm.DataPoints(q), pm.DataPoints(q), pm.Matches(np.zeros((1, 10), np.int32), d2))
+
+
+@pytest.mark.parametrize("name,kind", [("PointToPlaneErrorMinimizer", ob.E_POINT_TO_PLANE),
+                                       ("PointToPlaneWithCovErrorMinimizer", ob.E_POINT_TO_PLANE_WITH_COV),
+                                       ("PointToPointErrorMinimizer", ob.E_POINT_TO_POINT)])
+def test_error_minimizer_matches_oracle(pm, pair30k, name, kind):
+    rd, rf, _ = pair30k
+    oref = ob.Cloud(rf)
+    ob.apply_filter(oref, "SurfaceNormalDataPointsFilter", knn=10)
+    ord_ = ob.Cloud(rd)
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    st, w = ob.outlier_weights([{"TrimmedDistOutlierFilter": {"ratio": 0.85}}], d2)
+    st, want = ob.minimize(kind, ord_, oref, ids, d2, w)
+    assert st == 0
+    ref = pm.DataPoints(rf, {"normals": oref.desc("normals")})
+    e = pm.ErrorMinimizer(name)
+    T = e.compute(pm.DataPoints(rd), ref, w, pm.Matches(ids, d2))
+    np.testing.assert_allclose(T, want["T"], rtol=0, atol=1e-11)
+    assert e._last.kept == want["kept"]
+    assert e._last.weighted_point_used_ratio == pytest.approx(want["weighted_point_used_ratio"], rel=1e-15)
+    assert e._last.residual == pytest.approx(want["residual"], rel=1e-11)
+    if kind == ob.E_POINT_TO_PLANE_WITH_COV:
+        np.testing.assert_allclose(e.getCovariance(), want["cov"], rtol=1e-8, atol=1e-18)
+
+
+# ------------------------------------------------------------------ ICP (A15-A16) ---
+def _run_both(pm, cfg, rd, rf, T0=None, rd_desc=None):
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(cfg))
+    T = icp(pm.DataPoints(rd, rd_desc), pm.DataPoints(rf), T0)
+    want = ob.icp_run(cfg, ob.Cloud(rd, rd_desc), ob.Cloud(rf), T0)
+    return icp, T, want
+
+
+def test_icp_c1_point_to_point_30k(pm, pair30k):
+    rd, rf, _ = pair30k
+    icp, T, want = _run_both(pm, util.C1, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.errorMinimizer.getOverlap() == pytest.approx(want["overlap"], rel=1e-12)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_icp_c2_point_to_plane_120k(pm, seed):
+    rd, rf, truth = synth.scan_pair(seed, beams=64, az_steps=1875)
+    icp, T, want = _run_both(pm, util.C2, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    assert icp.getMaxNumIterationsReached() == want["max_iter_reached"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["residual"] == pytest.approx(want["residual"], rel=1e-7)
+    assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+    # and ICP did its job: within a few mm of the generating pose
+    assert np.abs(T[:3, 3] - truth[:3, 3]).max() < 0.02
+
+
+def test_icp_with_cov_and_initial_guess(pm, pair30k):
+    rd, rf, truth = pair30k
+    T0 = synth.pose_matrix(truth[:3, 3] + [0.05, -0.03, 0.01], 0.01, 0.0, 0.0)
+    T0[:3, :3] = truth[:3, :3] @ T0[:3, :3]
+    icp, T, want = _run_both(pm, util.C2_COV, rd, rf, T0)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    cov = icp.errorMinimizer.getCovariance()
+    np.testing.assert_allclose(cov, want["cov"], rtol=1e-6, atol=1e-16)
+    assert np.all(np.diag(cov) > 0)
+
+
+def test_icp_overlap_with_sensor_noise_descriptors(pm, pair30k):
+    rd, rf, _ = pair30k
+    oc = ob.Cloud(rd)
+    for it in util.INPUT_FILTERS:
+        (name, p), = ob._modlist([it])
+        ob.apply_filter(oc, name, **p)
+    desc = oc.descriptors()
+    icp, T, want = _run_both(pm, util.C2, rd, rf, rd_desc=desc)
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert 0.0 < want["overlap"] < 1.0
+    assert icp.errorMinimizer.getOverlap() == pytest.approx(want["overlap"], abs=1e-12)
+
+
+def test_icp_c5_voxel_reading_trimmed_075(pm, pair120k):
+    rd, rf, _ = pair120k
+    icp, T, want = _run_both(pm, util.C5, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    assert icp.last["n_reading"] < rd.shape[1]
+    util.assert_pose_close(T, want["T"])
+
+
+def test_icp_identical_clouds_gives_identity(pm, pair30k):
+    _, rf, _ = pair30k
+    # every match distance is 0 -> "no outlier to filter" with a trimmed filter
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rf), pm.DataPoints(rf))
+    assert ob.icp_run(util.C2, ob.Cloud(rf), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+    # without outlier filters the x = 0 solution takes the NaN -> identity branch (A.5)
+    cfg = dict(util.C2, outlierFilters=[])
+    icp, T, want = _run_both(pm, cfg, rf, rf)
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    np.testing.assert_allclose(T, np.eye(4), atol=1e-6)
+
+
+def test_icp_errors(pm, pair30k):
+    rd, rf, _ = pair30k
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(dict(util.C2, referenceDataPointsFilters=[])))
+    with pytest.raises(pm.InvalidField):  # point-to-plane without normals
+        icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    icp.loadFromYaml(util.to_yaml(util.C1))
+    bad = np.eye(4)
+    bad[0, 0] = 2.0
+    with pytest.raises(pm.TransformationError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rf), bad)
+    bound = dict(util.C1, transformationCheckers=util.CHECKERS + [
+        {"BoundTransformationChecker": {"maxRotationNorm": 0.001, "maxTranslationNorm": 0.001}}])
+    icp.loadFromYaml(util.to_yaml(bound))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    assert ob.icp_run(bound, ob.Cloud(rd), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+
+
+def test_icp_max_iterations_reached_flag(pm, pair30k):
+    rd, rf, _ = pair30k
+    cfg = dict(util.C1, transformationCheckers=[{"CounterTransformationChecker": {"maxIterationCount": 3}}])
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert icp.last["iterations"] == want["iterations"] == 3
+    assert icp.getMaxNumIterationsReached() and want["max_iter_reached"]
+    util.assert_pose_close(T, want["T"])
+
+
+def test_icp_sequence_set_map(pm, pair30k):
+    rd, rf, truth = pair30k
+    seq = pm.ICPSequence()
+    seq.loadFromYaml(util.to_yaml(util.C2))
+    assert not seq.hasMap()
+    seq.setMap(pm.DataPoints(rf))
+    assert seq.hasMap()
+    oseq = ob.IcpSequence(util.C2)
+    assert oseq.set_map(ob.Cloud(rf)) == 0
+    T_prev = np.eye(4)
+    for step in range(2):
+        T = seq(pm.DataPoints(rd), T_prev)
+        want = oseq.run(ob.Cloud(rd), T_prev)
+        assert seq.last["iterations"] == want["iterations"]
+        util.assert_pose_close(T, want["T"])
+        T_prev = want["T"]
+
+
+def test_batch_equals_single_runs(pm):
+    pairs = [synth.scan_pair(s, beams=16, az_steps=900 + 100 * s) for s in range(5)]  # ragged sizes
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    rds = [pm.DataPoints(p[0]) for p in pairs]
+    rfs = [pm.DataPoints(p[1]) for p in pairs]
+    batch = icp.compute_batch(rds, rfs)
+    for i, p in enumerate(pairs):
+        T = icp(rds[i], rfs[i])
+        assert np.array_equal(T, batch[i]["T"])  # independent of batching, bit for bit
+        assert icp.last["iterations"] == batch[i]["iterations"]
+        want = ob.icp_run(util.C2, ob.Cloud(p[0]), ob.Cloud(p[1]))
+        assert batch[i]["iterations"] == want["iterations"]
+        util.assert_pose_close(batch[i]["T"], want["T"])
+
+
+def test_probes_match_module_by_module_calls(pm, pair30k):
+    rd, rf, truth = pair30k
+    oref = ob.Cloud(rf)
+    ob.apply_filter(oref, "SurfaceNormalDataPointsFilter", knn=10)
+    ref = pm.DataPoints(rf, {"normals": oref.desc("normals")})
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    # Localizer::ComputeOverlapWith
+    got = icp.probe_overlap(pm.DataPoints(rd), pm.DataPoints(rf), truth)
+    st, want = ob.probe_overlap(util.C2, ob.Cloud(rd), ob.Cloud(rf), truth)
+    assert st == 0 and got == pytest.approx(want, rel=1e-15)
+    # the same, spelled the way Localizer.hpp:309-347 spells it
+    tmp = pm.ICP()
+    tmp.loadFromYaml(util.to_yaml(util.C2))
+    reference = pm.DataPoints(rf)
+    tmp.referenceDataPointsFilters.init()
+    tmp.referenceDataPointsFilters.apply(reference)
+    tmp.matcher.init(reference)
+    reading = pm.DataPoints(rd)
+    tmp.readingDataPointsFilters.init()
+    tmp.readingDataPointsFilters.apply(reading)
+    reading = pm.RigidTransformation().compute(reading, truth)
+    tmp.readingStepDataPointsFilters.init()
+    tmp.readingStepDataPointsFilters.apply(reading)
+    matches = tmp.matcher.findClosests(reading)
+    weights = tmp.outlierFilters.compute(reading, reference, matches)
+    ee = tmp.errorMinimizer.errorElements(reading, reference, weights, matches)
+    assert ee.weightedPointUsedRatio == pytest.approx(want, rel=1e-15)
+    # LoopCloser::ComputeResidualError
+    got = icp.probe_residual(pm.DataPoints(rd), ref, truth)
+    st, want = ob.probe_residual(util.C2, ob.Cloud(rd), oref, truth)
+    assert st == 0 and got == pytest.approx(want, rel=1e-10)
+
+
+def test_assemble_local_map(pm, pair30k):
+    rd, rf, truth = pair30k
+    a, b = pm.DataPoints(rf), pm.DataPoints(rd)
+    out = pm.assemble_local_map([a, b], [np.eye(4), truth])
+    oc = ob.Cloud(rd)
+    ob.rigid_transform(oc, truth)
+    assert out.getNbPoints() == rf.shape[1] + rd.shape[1]
+    assert np.array_equal(out.features[:, :rf.shape[1]], rf)
+    assert np.array_equal(out.features[:, rf.shape[1]:].view(np.uint32), oc.features.view(np.uint32))
