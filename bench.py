@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — ICP registrations/s on 120k-point scan pairs (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] — synthetic 64-beam
+120 000-point scan pair, point-to-plane ICP with the SurfaceNormal(knn=10)
+reference filter, KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, Counter(40) +
+Differential checkers.  One "step" = one pass of the whole registration path
+(reference filter -> index build -> ICP loop -> result) over one batch of
+`--pairs` distinct pairs per GPU; pairs are independent, so N GPUs each take
+their own batch (weak scaling) and only the per-pair 4x4 results are gathered
+(NCCL all_gather), inside the timed region.
+
+  value : registrations/s with the clouds already resident in HBM
+  e2e   : the same through the public API from pinned HOST buffers (H2D of
+          both clouds and D2H of the result inside the timed region)
+  roofline : the dominant kernel (match = fused transform + exact kNN), against
+          the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (a port of the libpointmatcher/libnabo path) on
+          this box's host cores, same workload, bounded sample
+
+`--impl reference` times that CPU path alone (the reference's libpointmatcher
+cannot be built here: un-vendored, un-pinned, absent — DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "icp_registrations_per_s_120k_pt_pairs"
+UNIT = "registrations/s"
+WORKLOAD = ("C2: synthetic 64-beam 120000-pt scan pair, point-to-plane ICP, SurfaceNormal(knn=10) reference "
+            "filter, KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, Counter(40)+Differential(1e-3,1e-3,3)")
+
+
+def c2_config():
+    from tests import util
+    return util.C2
+
+
+def gen_pair(seed):
+    from pgslam_b200 import synth
+    rd, rf, _ = synth.scan_pair(seed, beams=64, az_steps=1875)
+    return rd, rf
+
+
+def gen_pairs(seeds):
+    """Distinct synthetic pairs; generated in parallel on the host cores."""
+    seeds = list(seeds)
+    if len(seeds) <= 2:
+        return [gen_pair(s) for s in seeds]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(len(seeds), os.cpu_count() or 1)) as pool:
+        return pool.map(gen_pair, seeds)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(steps, warmup, sample_pairs=1):
+    """The CPU path (oracle port) on all host threads: one registration per step."""
+    from oracle import binding as ob
+    cfg = ob.config_from_dict(c2_config())
+    pairs = gen_pairs(range(1000, 1000 + sample_pairs))
+    clouds = [(ob.Cloud(rd), ob.Cloud(rf)) for rd, rf in pairs]
+    threads = ob.lib().orc_num_threads()
+    its = []
+    for i in range(warmup):
+        ob.icp_run(cfg, *clouds[i % len(clouds)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        r = ob.icp_run(cfg, *clouds[i % len(clouds)])
+        its.append(r["iterations"])
+    dt = time.perf_counter() - t0
+    return dict(value=steps / dt, seconds=dt, cores=threads, iterations=its,
+                sample=f"{steps} registration(s) of the same C2 workload ({len(clouds)} distinct pair(s)), "
+                       f"OpenMP over queries on {threads} host thread(s)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=48, help="distinct pairs per GPU per step")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="registrations for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(max(args.steps, 1), args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 points / f64 reductions",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "points_per_scan": 120000},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "iterations": r["iterations"]}
+        print(json.dumps(line))
+        return
+
+    # --------------------------------------------------------------------- ours
+    import torch
+    import torch.distributed as dist
+    from pgslam_b200 import build, pm
+    from tests import util
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    ctx = pm.Context(local_rank, stream.cuda_stream)
+    icp = pm.ICP(ctx)
+    icp.loadFromYaml(util.to_yaml(c2_config()))
+
+    B = args.pairs
+    pairs = gen_pairs(range(rank * B, rank * B + B))
+    n_pts = pairs[0][0].shape[1]
+    in_bytes = sum(rd.nbytes + rf.nbytes for rd, rf in pairs)
+    # pinned host copies for the e2e leg (point-major float32, exactly what the ABI takes)
+    host = [(torch.from_numpy(np.ascontiguousarray(rd.T)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rf.T)).pin_memory())
+            for rd, rf in pairs]
+    dev_rd = [pm.DataPoints(ctx=ctx, device_ptr=None, features=rd) for rd, _ in pairs]
+    dev_rf = [pm.DataPoints(ctx=ctx, device_ptr=None, features=rf) for _, rf in pairs]
+
+    gathered = torch.empty((world * B, 16), dtype=torch.float64, device="cuda") if multi else None
+
+    def gather(results):
+        """the path's only exchange step: per-pair transforms to every rank"""
+        if not multi:
+            return
+        loc = torch.tensor(np.stack([r["T"].ravel(order="F") for r in results]), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(gathered, loc)
+
+    def step_resident():
+        res = icp.compute_batch(dev_rd, dev_rf)
+        gather(res)
+        return res
+
+    def step_e2e():
+        rds, rfs = [], []
+        L = ctx.lib
+        import ctypes as C
+        for hrd, hrf in host:
+            for src, dst in ((hrd, rds), (hrf, rfs)):
+                h = C.c_void_p()
+                ctx.check(L.pgs_cloud_create(ctx.h, C.c_void_p(src.data_ptr()), src.shape[0], 0, C.byref(h)))
+                dst.append(pm.DataPoints(ctx=ctx, _handle=h))
+        res = icp.compute_batch(rds, rfs)
+        gather(res)
+        return res
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if multi:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ctx.set_profiling(True)
+    ms, res = timed(step_resident, args.steps)
+    stage = ctx.stage_times()  # of the last step
+    ctx.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # single-pair latency (batch of 1), for the record
+    one_rd, one_rf = [dev_rd[0]], [dev_rf[0]]
+    for _ in range(3):
+        icp.compute_batch(one_rd, one_rf)
+    ms_one, _ = timed(lambda: icp.compute_batch(one_rd, one_rf), 10)
+
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+
+    total_pairs = world * B
+    value = total_pairs * args.steps / (ms / 1e3)
+    e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
+    iters = [r["iterations"] for r in res]
+    ok = sum(r["status"] == 0 for r in res)
+    # roofline of the dominant kernel (match): algorithmic bytes = per query 16 B
+    # read + 8 B match written, plus one pass over the reference (16 B/pt) per
+    # launch and pair; only pairs still iterating do work.
+    n_ref = res[0]["n_reference"]
+    alg_bytes = sum(r["iterations"] * (24.0 * r["n_reading"] + 16.0 * r["n_reference"]) for r in res)
+    match_s = stage["match_ms"] / 1e3
+    peak, peak_src = peaks()
+    achieved = alg_bytes / match_s / 1e9 if match_s > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "match_kernel (fused rigid transform + exact k=1 NN traversal)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launches": stage["iterations_launched"],
+                "avg_launch_ms": stage["match_ms"] / max(stage["iterations_launched"], 1),
+                "algorithmic_bytes_per_step": alg_bytes,
+                "stage_ms_last_step": {k: round(float(v), 3) for k, v in stage.items()}}
+    reg_bytes = 68.0 * n_ref + 32.0 * n_pts + statistics.mean(iters) * ((32 + 32 * 0.85) * n_pts + 16.0 * n_ref)
+    roofline["whole_registration"] = {"algorithmic_bytes": reg_bytes, "achieved_gbs": reg_bytes * value / world / 1e9,
+                                      "frac": reg_bytes * value / world / 1e9 / peak}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        n = args.cpu_steps or 12
+        r = cpu_reference_run(n, 1, sample_pairs=min(4, n))
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 points / f64 reductions", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "points_per_scan": n_pts,
+                       "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
+                       "parallelism": f"{world} GPU(s), independent pairs per rank, NCCL all_gather of 4x4 results"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
+                    "d2h_bytes_per_step": int(total_pairs * 480), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "iterations_mean": statistics.mean(iters), "pairs_ok": ok,
+            "single_pair_latency_ms": ms_one / 10.0}
+    print(json.dumps(line))
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,15 @@ constexpr float kInfF = __builtin_inff();
 
 __host__ __device__ inline int tri(int c, int r) { return c * (c + 1) / 2 + r; }  // r <= c
 
+// number of blocks that reduce a cloud of n points: a function of n alone, so
+// that fp64 sums are bit-identical whatever batch the cloud is processed in
+__host__ __device__ inline int reduce_slices(int n, int per_block, int max_blocks) {
+  int s = (n + per_block - 1) / per_block;
+  return s < 1 ? 1 : (s > max_blocks ? max_blocks : s);
+}
+constexpr int kAccPerBlock = 1024;
+constexpr int kAccMaxBlocks = 128;
+
 // ---------------------------------------------------------------------------
 // per-pair accumulation of one weighted match (A.5 / A.7), all in fp64
 // ---------------------------------------------------------------------------
@@ -247,11 +256,13 @@ mean_kernel(const float4* const* __restrict__ pts, const int* __restrict__ ns, d
   __shared__ bool last;
   const int b = blockIdx.y;
   const int n = ns[b];
+  // the summation order must depend on this cloud only, never on what else is
+  // in the batch: the number of slices is a function of n alone
+  const unsigned slices = (unsigned)reduce_slices(n, 2048, 64);
+  if (blockIdx.x >= slices) return;
   const float4* p = pts[b];
   double s[3] = {0.0, 0.0, 0.0};
-  // contiguous slice per block, strided inside: any order is fine in fp64 as
-  // long as it is FIXED, which it is (grid size depends only on the batch)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += slices * blockDim.x) {
     float4 v = p[i];
     s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z;
   }
@@ -266,13 +277,13 @@ mean_kernel(const float4* const* __restrict__ pts, const int* __restrict__ ns, d
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(&tickets[b], 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(&tickets[b], 1u) == slices - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
   if (threadIdx.x < 3) {
     double t = 0.0;
-    for (unsigned j = 0; j < gridDim.x; ++j) t += __ldcg(&partials[((size_t)b * gridDim.x + j) * 3 + threadIdx.x]);
+    for (unsigned j = 0; j < slices; ++j) t += __ldcg(&partials[((size_t)b * gridDim.x + j) * 3 + threadIdx.x]);
     shift[4 * b + threadIdx.x] = n > 0 ? (float)(t / (double)n) : 0.f;
   }
   if (threadIdx.x == 3) shift[4 * b + 3] = 0.f;
@@ -475,12 +486,14 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
   PairState& st = states[blockIdx.y];
   if (!st.active) return;
   const PairView v = views[blockIdx.y];
+  const unsigned slices = (unsigned)reduce_slices(v.n_r, kAccPerBlock, kAccMaxBlocks);
+  if (blockIdx.x >= slices) return;
   const Xf T = st.xf;
   const float lo = st.lim_lo, hi = st.lim_hi;
   double acc[kAcc];
 #pragma unroll
   for (int j = 0; j < kAcc; ++j) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += slices * blockDim.x) {
     const int pos = v.match_pos[i];
     const float d = v.match_d2[i];
     // ErrorElements skips dist == inf; OutlierFilters weights are 0/1 here
@@ -511,13 +524,13 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == slices - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
   if (threadIdx.x < 30) {
     double t = 0.0;
-    for (unsigned j = 0; j < gridDim.x; ++j) t += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
+    for (unsigned j = 0; j < slices; ++j) t += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
     tot[threadIdx.x] = t;
   }
   __syncthreads();
@@ -537,6 +550,8 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
   PairState& st = states[blockIdx.y];
   if (st.status != PGS_OK || st.iterations == 0) return;
   const PairView v = views[blockIdx.y];
+  const unsigned slices = (unsigned)reduce_slices(v.n_r, kAccPerBlock, kAccMaxBlocks);
+  if (blockIdx.x >= slices) return;
   const Xf T = st.xf_prev;
   const float lo = st.lim_lo, hi = st.lim_hi;
   const bool want_cov = P.minimizer == MIN_P2PLANE_COV;
@@ -553,7 +568,7 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
   double acc[kAcc2];
 #pragma unroll
   for (int j = 0; j < kAcc2; ++j) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += slices * blockDim.x) {
     const int pos = v.match_pos[i];
     const float d = v.match_d2[i];
     bool use = pos >= 0 && d < kInfF;
@@ -591,13 +606,13 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket2, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket2, 1u) == slices - 1);
   __syncthreads();
   if (!last) return;
   __threadfence();
   if (threadIdx.x < kAcc2) {
     double s = 0.0;
-    for (unsigned j = 0; j < gridDim.x; ++j) s += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
+    for (unsigned j = 0; j < slices; ++j) s += __ldcg(&v.partials[(size_t)j * kAcc2 + threadIdx.x]);
     st.acc2[threadIdx.x] = s;
   }
   if (threadIdx.x == 0) st.ticket2 = 0;
@@ -907,7 +922,7 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     DBuf<int> d_n(ctx, B);
     ctx->upload_small(d_pts.p, pts.data(), sizeof(float4*) * B);
     ctx->upload_small(d_n.p, ns.data(), sizeof(int) * B);
-    const int nb = std::max(1, std::min(ceil_div(max_n, 2048), 64));
+    const int nb = reduce_slices(max_n, 2048, 64);
     DBuf<double> partials(ctx, (size_t)B * nb * 3);
     DBuf<unsigned> tickets(ctx, B);
     tickets.zero();
@@ -959,23 +974,17 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
 void IcpEngine::run_batch(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
                           const double* T_inits, pgs_icp_result* results) {
   const int P = (int)readings.size();
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx_->profiling) {
-    PGS_CUDA(cudaEventCreate(&e0));
-    PGS_CUDA(cudaEventCreate(&e1));
-    PGS_CUDA(cudaEventRecord(e0, ctx_->stream));
+    for (auto& e : idx_ev_)
+      if (!e) PGS_CUDA(cudaEventCreate(&e));
+    PGS_CUDA(cudaEventRecord(idx_ev_[0], ctx_->stream));
   }
   std::vector<std::unique_ptr<Cloud>> refs(P);
   for (int p = 0; p < P; ++p) refs[p] = references[p]->clone();
   std::vector<std::unique_ptr<PreparedRef>> prepared;
   prepare_references(refs, false, prepared);
-  if (ctx_->profiling) {
-    PGS_CUDA(cudaEventRecord(e1, ctx_->stream));
-    PGS_CUDA(cudaEventSynchronize(e1));
-    PGS_CUDA(cudaEventElapsedTime(&ctx_->times.index_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  }
+  if (ctx_->profiling) PGS_CUDA(cudaEventRecord(idx_ev_[1], ctx_->stream));
+  have_idx_ev_ = ctx_->profiling;
   std::vector<const PreparedRef*> rp(P);
   for (int p = 0; p < P; ++p) rp[p] = prepared[p].get();
   run_prepared(readings, rp, T_inits, results);
@@ -1069,7 +1078,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   }
 
   // ---- per-pair views ----------------------------------------------------------
-  const int acc_blocks = std::max(1, std::min(ceil_div(max_nr, 1024), ctx->num_sms));
+  const int acc_blocks = reduce_slices(max_nr, kAccPerBlock, kAccMaxBlocks);
   std::vector<PairView> hv(P);
   std::vector<DBuf<int>> mpos(P);
   std::vector<DBuf<float>> md2(P);
@@ -1113,6 +1122,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   *ctx->h_progress = (n_active == 0) ? 1 : 0;
   if (ctx->profiling) PGS_CUDA(cudaEventRecord(ev[1], s));
   int launched = 0;
+  std::vector<cudaEvent_t> kev;  // profiling only: 4 marks per iteration
   const int max_it = prm.hard_iteration_cap;
   const dim3 gm(ceil_div(std::max(max_nr, 1), 128), P), ga(acc_blocks, P);
   for (int it = 0; it < max_it; ++it) {
@@ -1122,9 +1132,20 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       PGS_CUDA(cudaEventSynchronize(ctx->loop_ev[it & 1]));
       if (*ctx->h_progress) break;
     }
+    auto mark = [&]() {
+      if (!ctx->profiling) return;
+      cudaEvent_t e;
+      PGS_CUDA(cudaEventCreate(&e));
+      PGS_CUDA(cudaEventRecord(e, s));
+      kev.push_back(e);
+    };
+    mark();
     match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+    mark();
     if (prm.n_quant > 0) select_kernel<<<P, 1024, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    mark();
     accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    mark();
     ctx_count_launches(ctx, prm.n_quant > 0 ? 3 : 2);
     PGS_CUDA(cudaEventRecord(ctx->loop_ev[it & 1], s));
     ++launched;
@@ -1168,6 +1189,20 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     PGS_CUDA(cudaEventElapsedTime(&t.loop_ms, ev[1], ev[2]));
     PGS_CUDA(cudaEventElapsedTime(&t.total_ms, ev[0], ev[3]));
     t.iterations_launched = launched;
+    t.index_ms = 0.f;
+    if (have_idx_ev_) PGS_CUDA(cudaEventElapsedTime(&t.index_ms, idx_ev_[0], idx_ev_[1]));
+    have_idx_ev_ = false;
+    t.match_ms = t.select_ms = t.accumulate_ms = 0.f;
+    for (size_t i = 0; i + 3 < kev.size(); i += 4) {
+      float a = 0, b = 0, c = 0;
+      PGS_CUDA(cudaEventElapsedTime(&a, kev[i], kev[i + 1]));
+      PGS_CUDA(cudaEventElapsedTime(&b, kev[i + 1], kev[i + 2]));
+      PGS_CUDA(cudaEventElapsedTime(&c, kev[i + 2], kev[i + 3]));
+      t.match_ms += a;
+      t.select_ms += b;
+      t.accumulate_ms += c;
+    }
+    for (auto& e : kev) cudaEventDestroy(e);
     for (auto& e : ev) cudaEventDestroy(e);
   }
 }

@@ -102,6 +102,8 @@ class IcpEngine {
   Ctx* ctx_;
   ChainConfig cfg_;
   std::unique_ptr<PreparedRef> map_;
+  cudaEvent_t idx_ev_[2] = {nullptr, nullptr};  // profiling: reference-side preparation
+  bool have_idx_ev_ = false;
 };
 
 // fine-grained modules (pgs_matcher / pgs_outliers / pgs_minimizer)
