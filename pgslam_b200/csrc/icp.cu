@@ -323,6 +323,9 @@ __global__ void init_state_kernel(PairState* __restrict__ states, const double* 
   for (int d = 0; d < 3; ++d) st.t0[d] = st.t[0][d];
   st.ticket = 0;
   st.ticket2 = 0;
+  st.ticket3 = 0;
+  st.sel_prefix = st.sel_mask = 0;
+  st.sel_rank = 0;
   st.kept = st.wsum = st.resid = st.overlap = 0.0;
   for (int i = 0; i < 36; ++i) st.cov[i] = 0.0;
   st.lim_lo = -kInfF;
@@ -401,80 +404,117 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   v.match_d2[i] = acc.d;
 }
 
-// exact quantile(s) of the valid match distances: 4-pass MSB radix select on
-// the fp32 bit patterns (non-negative floats order like unsigned ints)
-__global__ void __launch_bounds__(1024)
-select_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int* n_active,
-              volatile int* h_done) {
-  __shared__ unsigned hist[256];
-  __shared__ unsigned s_prefix, s_mask, s_fail;
-  __shared__ unsigned long long s_rank;
-  PairState& st = states[blockIdx.x];
+// Exact quantile of the valid match distances (Matches::getDistsQuantile, A.3)
+// as a 3-pass MSB radix select over the fp32 bit patterns (11 + 11 + 10 bits;
+// non-negative floats order like unsigned ints).  Each pass is one multi-block
+// kernel: blocks histogram their slice in shared memory, merge into the pair's
+// global 2048-bin histogram, and the last block to finish picks the digit that
+// holds the wanted rank.  An exact order statistic is algorithm-independent, so
+// the limit is bit-identical to the reference's nth_element.
+constexpr int kSelBins = 2048;
+constexpr int kSelBlocks = 16;
+
+__global__ void __launch_bounds__(256)
+select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int jq, int pass,
+                   int* n_active, volatile int* h_done) {
+  __shared__ unsigned hist[kSelBins];
+  __shared__ unsigned lane_tot[32];
+  __shared__ bool last;
+  PairState& st = states[blockIdx.y];
   if (!st.active) return;
-  const PairView v = views[blockIdx.x];
+  const PairView v = views[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31;
-  float hi = P.fixed_hi, lo = P.fixed_lo;
-  for (int jq = 0; jq < P.n_quant; ++jq) {
-    if (tid == 0) { s_prefix = 0; s_mask = 0; s_fail = 0; s_rank = 0; }
-    __syncthreads();
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      if (tid < 256) hist[tid] = 0;
-      __syncthreads();
-      const unsigned prefix = s_prefix, mask = s_mask;
-      for (int base = 0; base < v.n_r; base += 1024) {
-        const int i = base + tid;
-        unsigned u = 0;
-        bool valid = false;
-        if (i < v.n_r) {
-          u = __float_as_uint(v.match_d2[i]);
-          // getDistsQuantile: dist != inf and dist > 0 (A.3)
-          valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
-        }
-        unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-          unsigned d = (u >> shift) & 255u;
-          unsigned m = __match_any_sync(act, d);
-          if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        unsigned long long rank = s_rank;
-        if (pass == 0) {
-          unsigned long long M = 0;
-          for (int d = 0; d < 256; ++d) M += hist[d];
-          if (M == 0) s_fail = 1;
-          const double q = P.q_ratio[jq];
-          rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
-          if (M && rank >= M) rank = M - 1;
-        }
-        unsigned long long cum = 0;
-        int d = 0;
-        for (; d < 255; ++d) {
-          if (cum + hist[d] > rank) break;
-          cum += hist[d];
-        }
-        s_rank = rank - cum;
-        s_prefix = prefix | ((unsigned)d << shift);
-        s_mask = mask | (255u << shift);
-      }
-      __syncthreads();
-      if (s_fail) break;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  const unsigned dmask = pass == 2 ? 1023u : 2047u;
+  const unsigned prefix = pass == 0 ? 0u : st.sel_prefix;
+  const unsigned mask = pass == 0 ? 0u : st.sel_mask;
+  for (int d = tid; d < kSelBins; d += 256) hist[d] = 0;
+  __syncthreads();
+  for (int base = blockIdx.x * 256; base < v.n_r; base += gridDim.x * 256) {
+    const int i = base + tid;
+    unsigned u = 0;
+    bool valid = false;
+    if (i < v.n_r) {
+      u = __float_as_uint(v.match_d2[i]);
+      // getDistsQuantile: dist != inf and dist > 0
+      valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
     }
-    if (s_fail) {
-      if (tid == 0) {  // "no outlier to filter"
-        st.status = PGS_CONVERGENCE_ERROR;
-        st.active = 0;
-        pair_finished(n_active, h_done);
-      }
-      return;
+    unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      unsigned d = (u >> shift) & dmask;
+      unsigned m = __match_any_sync(act, d);
+      if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
     }
-    float limit = __fmul_rn(P.q_factor[jq], __uint_as_float(s_prefix));
-    hi = fminf(hi, limit);
-    __syncthreads();
   }
-  if (tid == 0) { st.lim_lo = lo; st.lim_hi = hi; }
+  __syncthreads();
+  for (int d = tid; d < kSelBins; d += 256)
+    if (hist[d]) atomicAdd(&v.sel_hist[d], hist[d]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(&st.ticket3, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the last block owns the merged histogram: read it, then clear it for the next pass
+  for (int d = tid; d < kSelBins; d += 256) {
+    hist[d] = __ldcg(&v.sel_hist[d]);
+    v.sel_hist[d] = 0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    unsigned t = 0;
+    for (int d = lane * 64; d < lane * 64 + 64; ++d) t += hist[d];
+    lane_tot[lane] = t;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    st.ticket3 = 0;
+    unsigned long long rank = st.sel_rank;
+    bool fail = false;
+    if (pass == 0) {
+      unsigned long long M = 0;
+      for (int l = 0; l < 32; ++l) M += lane_tot[l];
+      if (M == 0) fail = true;
+      const double q = P.q_ratio[jq];
+      rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
+      if (M && rank >= M) rank = M - 1;
+    }
+    if (fail) {  // "no outlier to filter"
+      st.status = PGS_CONVERGENCE_ERROR;
+      st.active = 0;
+      pair_finished(n_active, h_done);
+    } else {
+      unsigned long long cum = 0;
+      int l = 0;
+      for (; l < 31; ++l) {
+        if (cum + lane_tot[l] > rank) break;
+        cum += lane_tot[l];
+      }
+      int d = l * 64;
+      for (; d < l * 64 + 63; ++d) {
+        if (cum + hist[d] > rank) break;
+        cum += hist[d];
+      }
+      st.sel_rank = rank - cum;
+      const unsigned np = prefix | ((unsigned)d << shift);
+      st.sel_prefix = np;
+      st.sel_mask = mask | (dmask << shift);
+      if (pass == 2) {
+        const float limit = __fmul_rn(P.q_factor[jq], __uint_as_float(np));
+        const float hi = jq == 0 ? P.fixed_hi : st.lim_hi;
+        st.lim_hi = fminf(hi, limit);
+        st.lim_lo = P.fixed_lo;
+      }
+    }
+  }
+}
+
+// no quantile-based filter in the chain: the limits are the fixed ones
+__global__ void fixed_limits_kernel(PairState* __restrict__ states, IcpParams P, int n_pairs) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  states[p].lim_hi = P.fixed_hi;
+  states[p].lim_lo = P.fixed_lo;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1083,6 +1123,8 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   std::vector<DBuf<int>> mpos(P);
   std::vector<DBuf<float>> md2(P);
   std::vector<DBuf<double>> partials(P);
+  DBuf<unsigned> sel_hist(ctx, (size_t)P * kSelBins);
+  sel_hist.zero();
   std::vector<DBuf<float4>> rdn(P);
   std::vector<DBuf<float>> rdnoise(P);
   for (int p = 0; p < P; ++p) {
@@ -1110,6 +1152,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     v.match_pos = mpos[p].p;
     v.match_d2 = md2[p].p;
     v.partials = partials[p].p;
+    v.sel_hist = sel_hist.p + (size_t)p * kSelBins;
     hv[p] = v;
   }
   DBuf<PairView> d_views(ctx, P);
@@ -1125,6 +1168,11 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   std::vector<cudaEvent_t> kev;  // profiling only: 4 marks per iteration
   const int max_it = prm.hard_iteration_cap;
   const dim3 gm(ceil_div(std::max(max_nr, 1), 128), P), ga(acc_blocks, P);
+  const dim3 gs(std::max(1, std::min(kSelBlocks, ceil_div(max_nr, 2048))), P);
+  if (prm.n_quant == 0) {
+    fixed_limits_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, P);
+    ctx_count_launches(ctx, 1);
+  }
   for (int it = 0; it < max_it; ++it) {
     if (*ctx->h_progress) break;
     if (it >= 2) {
@@ -1142,11 +1190,13 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     mark();
     match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
     mark();
-    if (prm.n_quant > 0) select_kernel<<<P, 1024, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    for (int jq = 0; jq < prm.n_quant; ++jq)
+      for (int pass = 0; pass < 3; ++pass)
+        select_pass_kernel<<<gs, 256, 0, s>>>(d_views.p, d_states.p, prm, jq, pass, d_nactive.p, ctx->d_progress);
     mark();
     accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
     mark();
-    ctx_count_launches(ctx, prm.n_quant > 0 ? 3 : 2);
+    ctx_count_launches(ctx, 2 + 3 * prm.n_quant);
     PGS_CUDA(cudaEventRecord(ctx->loop_ev[it & 1], s));
     ++launched;
   }

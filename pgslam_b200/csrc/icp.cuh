@@ -52,6 +52,9 @@ struct PairState {
   float lim_lo, lim_hi;
   unsigned ticket;   // last-block detection
   unsigned ticket2;
+  unsigned ticket3;  // select passes
+  unsigned sel_prefix, sel_mask;
+  unsigned long long sel_rank;
   double acc[kAcc];
   double acc2[kAcc2];
   double kept, wsum, resid, overlap;
@@ -68,6 +71,7 @@ struct PairView {
   int* match_pos;
   float* match_d2;
   double* partials;  // [grid.x][kAcc2]
+  unsigned* sel_hist;  // 2048 bins, zero between passes
 };
 
 // reference side of a registration, ready for matching

@@ -1,6 +1,10 @@
 // knn.cu — batched exact kNN kernels (generic k) on top of knn.cuh.
 // One thread per query; queries arrive in Morton order so the lanes of a warp
 // walk nearly the same nodes (broadcast loads, little divergence).
+//
+// k is a template parameter (the candidate list lives in registers); a request
+// for k neighbours runs the smallest instantiated K >= k and reports the first
+// k entries, which is exact because the K-list is sorted.
 #include "knn.cuh"
 
 namespace pgs {
@@ -14,48 +18,52 @@ struct KnnJobDev {
   int nq;
   int32_t* ids;
   float* d2;
+  int self;  // queries ARE tree.pts (self-kNN): seed from the Morton neighbourhood
 };
 
-template <int KCAP>
+template <int K>
 __global__ void __launch_bounds__(128)
 knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   const KnnJobDev job = jobs[blockIdx.y];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= job.nq) return;
-  float4 q = job.queries[j];
-  BestK<KCAP> acc;
-  acc.init(k);
-  knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc);
+  const float4 q = job.queries[j];
+  BestK<K> acc;
+  acc.init();
+  int skip_lo = 0, skip_hi = -1;
+  if (job.self) {
+    // neighbours in Morton order are mostly neighbours in space: they give a
+    // tight k-th distance before the tree is touched, so the walk prunes hard
+    skip_lo = max(0, j - K);
+    skip_hi = min(job.tree.n - 1, j + K);
+    for (int p = skip_lo; p <= skip_hi; ++p) {
+      float4 c = job.tree.pts[p];
+      float dd = dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
+      if (dd <= maxr2) acc.offer(dd, __float_as_int(c.w), p);
+    }
+  }
+  knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc, skip_lo, skip_hi);
   const int col = job.qperm ? job.qperm[j] : j;
   int32_t* oi = job.ids + (size_t)col * k;
   float* od = job.d2 + (size_t)col * k;
 #pragma unroll
-  for (int e = 0; e < KCAP; ++e) {
+  for (int e = 0; e < K; ++e) {
     if (e < k) {
-      oi[e] = (acc.id[e] == 0x7fffffff) ? -1 : acc.id[e];
-      od[e] = acc.d[e];
+      const int id = key_id(acc.key[e]);
+      oi[e] = (id == 0x7fffffff) ? -1 : id;
+      od[e] = key_dist(acc.key[e]);
     }
   }
-}
-
-template <>
-__global__ void __launch_bounds__(128)
-knn_kernel<1>(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
-  const KnnJobDev job = jobs[blockIdx.y];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= job.nq) return;
-  float4 q = job.queries[j];
-  Best1 acc;
-  acc.init();
-  knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc);
-  const int col = job.qperm ? job.qperm[j] : j;
-  job.ids[col] = (acc.pos < 0) ? -1 : acc.id;
-  job.d2[col] = acc.d;
 }
 
 __global__ void perm_from_sorted_kernel(const float4* __restrict__ pts, int n, int* __restrict__ perm) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) perm[j] = __float_as_int(pts[j].w);
+}
+
+template <int K>
+void launch_k(Ctx* ctx, dim3 grid, const KnnJobDev* d_jobs, int k, float maxr2) {
+  knn_kernel<K><<<grid, 128, 0, ctx->stream>>>(d_jobs, k, maxr2);
 }
 
 void launch(Ctx* ctx, const std::vector<KnnJobDev>& jobs, int k, float max_dist) {
@@ -69,10 +77,19 @@ void launch(Ctx* ctx, const std::vector<KnnJobDev>& jobs, int k, float max_dist)
   const float inf = __builtin_inff();
   float maxr2 = (max_dist == inf) ? inf : max_dist * max_dist;
   dim3 grid(ceil_div(max_q, 128), (unsigned)jobs.size());
-  if (k == 1) knn_kernel<1><<<grid, 128, 0, ctx->stream>>>(d_jobs.p, k, maxr2);
-  else if (k <= 8) knn_kernel<8><<<grid, 128, 0, ctx->stream>>>(d_jobs.p, k, maxr2);
-  else if (k <= 16) knn_kernel<16><<<grid, 128, 0, ctx->stream>>>(d_jobs.p, k, maxr2);
-  else knn_kernel<32><<<grid, 128, 0, ctx->stream>>>(d_jobs.p, k, maxr2);
+  if (k == 1) launch_k<1>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k == 2) launch_k<2>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k == 3) launch_k<3>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k == 4) launch_k<4>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k == 5) launch_k<5>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k == 6) launch_k<6>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 8) launch_k<8>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 10) launch_k<10>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 12) launch_k<12>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 16) launch_k<16>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 20) launch_k<20>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 24) launch_k<24>(ctx, grid, d_jobs.p, k, maxr2);
+  else launch_k<32>(ctx, grid, d_jobs.p, k, maxr2);
   ctx_count_launches(ctx, 1);
   PGS_LAUNCH_CHECK();
 }
@@ -81,7 +98,7 @@ void launch(Ctx* ctx, const std::vector<KnnJobDev>& jobs, int k, float max_dist)
 
 void knn_batched(Ctx* ctx, const std::vector<KnnJob>& jobs, int k, float max_dist) {
   std::vector<KnnJobDev> dj;
-  for (auto& j : jobs) dj.push_back(KnnJobDev{j.tree, j.queries, j.qperm, j.nq, j.ids, j.d2});
+  for (auto& j : jobs) dj.push_back(KnnJobDev{j.tree, j.queries, j.qperm, j.nq, j.ids, j.d2, 0});
   launch(ctx, dj, k, max_dist);
 }
 
@@ -98,7 +115,7 @@ void knn_self_batched(Ctx* ctx, const std::vector<const Index*>& idx, int k, flo
                                                                                  perms.back().p);
       ctx_count_launches(ctx, 1);
     }
-    dj.push_back(KnnJobDev{idx[b]->view(), idx[b]->pts.p, perms.back().p, idx[b]->n, ids[b], d2[b]});
+    dj.push_back(KnnJobDev{idx[b]->view(), idx[b]->pts.p, perms.back().p, idx[b]->n, ids[b], d2[b], 1});
   }
   launch(ctx, dj, k, max_dist);
 }

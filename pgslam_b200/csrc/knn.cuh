@@ -11,6 +11,10 @@
 // the bound never exceeds the distance of any point in the box.  Equal bounds
 // are visited because an equal distance with a lower index must still win.
 //
+// Candidates are kept as 64-bit keys (distance bits << 32 | index): squared
+// distances are non-negative, so their bit patterns order like the values and
+// one unsigned compare implements the (distance, index) lexicographic rule.
+//
 // Traversal state is two registers: the 1-based heap index of the current node
 // and a bit trail (bit j set = the sibling j levels up is still pending).  No
 // stack memory; a sibling's box is re-tested against the (tighter) bound when
@@ -22,6 +26,14 @@
 namespace pgs {
 
 #ifdef __CUDACC__
+
+constexpr unsigned long long kEmptyKey = 0x7f8000007fffffffull;  // (+inf, INT_MAX)
+
+__device__ __forceinline__ unsigned long long make_key(float d, int id) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)id;
+}
+__device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int key_id(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
 
 struct Best1 {
   float d;
@@ -38,84 +50,67 @@ struct Best1 {
   }
 };
 
-// ascending (d, id) list of capacity KCAP, of which the first k entries count
-template <int KCAP>
+// ascending list of exactly K keys, held in registers (all indices static)
+template <int K>
 struct BestK {
-  float d[KCAP];
-  int id[KCAP];
-  int k;
-  __device__ __forceinline__ void init(int kk) {
-    k = kk;
+  unsigned long long key[K];
+  __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int j = 0; j < KCAP; ++j) { d[j] = __int_as_float(0x7f800000); id[j] = 0x7fffffff; }
+    for (int j = 0; j < K; ++j) key[j] = kEmptyKey;
   }
-  __device__ __forceinline__ float bound() const {
-    float b = d[0];
-#pragma unroll
-    for (int j = 1; j < KCAP; ++j) b = (j == k - 1) ? d[j] : b;
-    return (k == 1) ? d[0] : b;
-  }
+  __device__ __forceinline__ float bound() const { return key_dist(key[K - 1]); }
   __device__ __forceinline__ void offer(float dd, int iid, int) {
-    // cheap reject against the k-th entry first
-    float bd = bound();
-    if (dd > bd) return;
-    int bid = id[0];
+    const unsigned long long nk = make_key(dd, iid);
+    if (nk >= key[K - 1]) return;  // the common case: one compare
 #pragma unroll
-    for (int j = 1; j < KCAP; ++j) bid = (j == k - 1) ? id[j] : bid;
-    if (dd == bd && iid >= bid) return;
-#pragma unroll
-    for (int j = KCAP - 1; j >= 1; --j) {
-      if (j < k) {
-        bool before_prev = dd < d[j - 1] || (dd == d[j - 1] && iid < id[j - 1]);
-        bool before_this = dd < d[j] || (dd == d[j] && iid < id[j]);
-        float nd = before_prev ? d[j - 1] : (before_this ? dd : d[j]);
-        int ni = before_prev ? id[j - 1] : (before_this ? iid : id[j]);
-        d[j] = nd;
-        id[j] = ni;
-      }
+    for (int j = K - 1; j >= 1; --j) {
+      const unsigned long long prev = key[j - 1];
+      key[j] = (nk < prev) ? prev : ((nk < key[j]) ? nk : key[j]);
     }
-    bool first = dd < d[0] || (dd == d[0] && iid < id[0]);
-    if (first) { d[0] = dd; id[0] = iid; }
+    if (nk < key[0]) key[0] = nk;
   }
 };
 
+// skip_lo..skip_hi: sorted positions already offered by the caller (self-kNN
+// window seeding); pass an empty range (0, -1) otherwise.
 template <class Acc>
 __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz, float maxr2,
-                                             Acc& acc) {
+                                             Acc& acc, int skip_lo = 0, int skip_hi = -1) {
   const float4* __restrict__ nodes4 = reinterpret_cast<const float4*>(t.nodes);
   unsigned node = 1, trail = 0;
   int depth = 0;
   while (true) {
-    bool descend = false;
-    if (depth == t.depth) {
-      const int leaf = (int)node - t.P;
-      if (leaf < t.n_leaves) {
-        const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
-#pragma unroll
-        for (int j = 0; j < kLeaf; ++j) {
-          float4 p = lp[j];
-          float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-          if (dd <= maxr2) acc.offer(dd, __float_as_int(p.w), leaf * kLeaf + j);
-        }
-      }
-    } else {
-      // both children: 12 consecutive floats at node*48 bytes
-      const float4* __restrict__ c = nodes4 + (size_t)node * 3;
+    // ---- descend while the nearer child qualifies -------------------------
+    bool at_leaf = true;
+    while (depth < t.depth) {
+      const float4* __restrict__ c = nodes4 + (size_t)node * 3;  // both children: 48 bytes
       float4 a = c[0], b = c[1], e = c[2];
       float lb0 = box_lb_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
       float lb1 = box_lb_rn(qx, qy, qz, b.z, b.w, e.x, e.y, e.z, e.w);
       float bound = fminf(acc.bound(), maxr2);
       bool near1 = lb1 < lb0;
       float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
-      if (lbn <= bound) {
-        trail = (trail << 1) | ((lbf <= bound) ? 1u : 0u);
-        node = node * 2 + (near1 ? 1u : 0u);
-        ++depth;
-        descend = true;
+      if (!(lbn <= bound)) { at_leaf = false; break; }
+      trail = (trail << 1) | ((lbf <= bound) ? 1u : 0u);
+      node = node * 2 + (near1 ? 1u : 0u);
+      ++depth;
+    }
+    // ---- leaf ----------------------------------------------------------------
+    if (at_leaf) {
+      const int leaf = (int)node - t.P;
+      if (leaf < t.n_leaves) {
+        const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
+        const int base = leaf * kLeaf;
+#pragma unroll
+        for (int j = 0; j < kLeaf; ++j) {
+          float4 p = lp[j];
+          float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+          const int pos = base + j;
+          if (dd <= maxr2 && (pos < skip_lo || pos > skip_hi)) acc.offer(dd, __float_as_int(p.w), pos);
+        }
       }
     }
-    if (descend) continue;
-    // walk back to the deepest pending sibling whose box still qualifies
+    // ---- walk back to the deepest pending sibling whose box still qualifies --
     while (true) {
       if (trail == 0) return;
       int up = __ffs(trail) - 1;

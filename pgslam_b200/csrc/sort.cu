@@ -5,11 +5,12 @@
 // order — VoxelGrid's "sum in input order" semantics
 // depend on that.
 //
-// Shape: 8 bits per pass, three kernels per pass (count, scan, scatter).  The
-// unit of work is a warp-chunk of 32*kSortRounds consecutive keys: a warp ranks
-// its chunk with __match_any_sync, so there is no block-level synchronisation
-// in the count or scatter kernels and ranks are stable by construction
-// (round-major, lane-minor == input order).
+// Shape: 8 bits per pass, three kernels per pass (count, scan, scatter).  A
+// block owns a tile of 8 warp-chunks (32*kSortRounds consecutive keys each); a
+// warp ranks its chunk with __match_any_sync (round-major, lane-minor == input
+// order, so ranks are stable by construction) and the block only meets twice,
+// to turn per-warp digit counts into offsets.  The scanned table is
+// 256 x tiles ints per job (a few thousand), not one row per warp.
 #include "core.cuh"
 
 namespace pgs {
@@ -18,21 +19,12 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
+// digit histogram of one warp-chunk into cnt[256] (warp-private shared memory)
 template <typename K>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-sort_count_kernel(const K* __restrict__ keys, const int* __restrict__ ns, int stride, int nchunks,
-                  int shift, int* __restrict__ counts) {
-  __shared__ int cnt[kWarpsPerBlock][256];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * kWarpsPerBlock + w;
-  if (c >= nchunks) return;
-  const int n = ns[b];
-  for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
+__device__ __forceinline__ void warp_chunk_count(const K* __restrict__ kp, int base, int n, int shift, int lane,
+                                                 int* __restrict__ cnt, K (&kreg)[kSortRounds]) {
+  for (int d = lane; d < 256; d += 32) cnt[d] = 0;
   __syncwarp();
-  const int base = c * kSortChunk;
-  const K* kp = keys + (size_t)b * stride + base;
-  K kreg[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     int i = base + r * 32 + lane;
@@ -46,11 +38,29 @@ sort_count_kernel(const K* __restrict__ keys, const int* __restrict__ ns, int st
     if (valid) {
       int d = (int)((kreg[r] >> shift) & 255);
       unsigned m = __match_any_sync(act, d);
-      if (lane == __ffs(m) - 1) cnt[w][d] += __popc(m);
+      if (lane == __ffs(m) - 1) cnt[d] += __popc(m);
     }
     __syncwarp();
   }
-  for (int d = lane; d < 256; d += 32) counts[((size_t)b * 256 + d) * nchunks + c] = cnt[w][d];
+}
+
+// one block = one tile of kWarpsPerBlock warp-chunks; counts[job][digit][tile]
+template <typename K>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sort_count_kernel(const K* __restrict__ keys, const int* __restrict__ ns, int stride, int ntiles,
+                  int shift, int* __restrict__ counts) {
+  __shared__ int cnt[kWarpsPerBlock][256];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int n = ns[b];
+  const int base = (tile * kWarpsPerBlock + w) * kSortChunk;
+  K kreg[kSortRounds];
+  warp_chunk_count<K>(keys + (size_t)b * stride + base, base, n, shift, lane, cnt[w], kreg);
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int j = 0; j < kWarpsPerBlock; ++j) t += cnt[j][threadIdx.x];
+  counts[((size_t)b * 256 + threadIdx.x) * ntiles + tile] = t;
 }
 
 // in-place exclusive scan of `total` ints per job; one block per job.
@@ -93,28 +103,36 @@ template <typename K>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sort_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                    const int* __restrict__ ns, int stride, int nchunks, int shift,
+                    const int* __restrict__ ns, int stride, int ntiles, int shift,
                     const int* __restrict__ offsets) {
   __shared__ int off[kWarpsPerBlock][256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * kWarpsPerBlock + w;
-  if (c >= nchunks) return;
+  const int b = blockIdx.y, tile = blockIdx.x;
   const int n = ns[b];
-  const int base = c * kSortChunk;
-  if (base >= n) return;
-  for (int d = lane; d < 256; d += 32) off[w][d] = offsets[((size_t)b * 256 + d) * nchunks + c];
-  __syncwarp();
+  if (tile * kWarpsPerBlock * kSortChunk >= n) return;
+  const int base = (tile * kWarpsPerBlock + w) * kSortChunk;
   const K* kp = keys_in + (size_t)b * stride + base;
   const uint32_t* vp = vals_in + (size_t)b * stride + base;
+  K kreg[kSortRounds];
+  warp_chunk_count<K>(kp, base, n, shift, lane, off[w], kreg);
+  __syncthreads();
+  {
+    // digit d: tile base from the scan, then an exclusive prefix over the warps
+    int run = offsets[((size_t)b * 256 + threadIdx.x) * ntiles + tile];
+#pragma unroll
+    for (int j = 0; j < kWarpsPerBlock; ++j) {
+      int t = off[j][threadIdx.x];
+      off[j][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
   K* ko = keys_out + (size_t)b * stride;
   uint32_t* vo = vals_out + (size_t)b * stride;
-  K kreg[kSortRounds];
   uint32_t vreg[kSortRounds];
 #pragma unroll
   for (int r = 0; r < kSortRounds; ++r) {
     int i = base + r * 32 + lane;
-    kreg[r] = (i < n) ? kp[r * 32 + lane] : K(0);
     vreg[r] = (i < n) ? vp[r * 32 + lane] : 0u;
   }
 #pragma unroll
@@ -243,18 +261,18 @@ template <typename K>
 bool radix_sort_pairs(Ctx* ctx, K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                       const int* d_n, int n_jobs, int stride, int max_n, int key_bits) {
   if (n_jobs == 0 || max_n == 0) return false;
-  const int nchunks = ceil_div(max_n, kSortChunk);
+  const int ntiles = ceil_div(max_n, kSortChunk * kWarpsPerBlock);
   const int passes = (key_bits + 7) / 8;
-  DBuf<int> counts(ctx, (size_t)n_jobs * 256 * nchunks);
-  dim3 grid(ceil_div(nchunks, kWarpsPerBlock), n_jobs);
+  DBuf<int> counts(ctx, (size_t)n_jobs * 256 * ntiles);
+  dim3 grid(ntiles, n_jobs);
   K* ki = keys_a;
   K* ko = keys_b;
   uint32_t* vi = vals_a;
   uint32_t* vo = vals_b;
   for (int p = 0; p < passes; ++p) {
-    sort_count_kernel<K><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ki, d_n, stride, nchunks, 8 * p, counts.p);
-    sort_scan_kernel<<<n_jobs, 1024, 0, ctx->stream>>>(counts.p, 256 * nchunks);
-    sort_scatter_kernel<K><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ki, vi, ko, vo, d_n, stride, nchunks,
+    sort_count_kernel<K><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ki, d_n, stride, ntiles, 8 * p, counts.p);
+    sort_scan_kernel<<<n_jobs, 1024, 0, ctx->stream>>>(counts.p, 256 * ntiles);
+    sort_scatter_kernel<K><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ki, vi, ko, vo, d_n, stride, ntiles,
                                                                          8 * p, counts.p);
     ctx_count_launches(ctx, 3);
     std::swap(ki, ko);
