@@ -201,6 +201,21 @@ pgs_status pgs_icp_probe_residual(pgs_icp *icp, const pgs_cloud *reading,
                                   const pgs_cloud *reference, const double T[16],
                                   double *residual);
 
+/* ---- configuration check (host only, no device needed) ---------------------- */
+/* Parses and validates a libpointmatcher YAML exactly as the loaders above do
+ * (ICPChainBase::loadFromYaml when is_chain != 0, DataPointsFilters(istream&)
+ * otherwise) without touching the GPU.  On failure the message is written
+ * NUL-terminated into err (cap bytes).  On success *n_modules receives the
+ * number of modules the configuration instantiates.                          */
+pgs_status pgs_config_check(const char *yaml, size_t len, int is_chain,
+                            int *n_modules, char *err, int cap);
+/* Registrar introspection: number of registered modules of a kind
+ * (0 DataPointsFilter, 1 Matcher, 2 OutlierFilter, 3 ErrorMinimizer,
+ * 4 TransformationChecker, 5 Inspector, 6 Logger, 7 Transformation) and the
+ * name of the i-th one.                                                       */
+int pgs_registrar_count(int kind);
+const char *pgs_registrar_name(int kind, int index);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context launched since creation (bench.py's
  * gpu_launches) and device milliseconds of the last ICP stage breakdown.     */

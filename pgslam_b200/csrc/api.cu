@@ -159,6 +159,48 @@ pgs_status pgs_ctx_synchronize(pgs_ctx* ctx) {
   PGS_API_END(&ctx->c)
 }
 
+pgs_status pgs_config_check(const char* yaml, size_t len, int is_chain, int* n_modules, char* err, int cap) {
+  int code = PGS_OK;
+  std::string msg;
+  try {
+    int n = 0;
+    if (is_chain) {
+      ChainConfig c = chain_from_yaml(std::string(yaml, len));
+      params_from_chain(c);  // also rejects combinations the device path does not implement
+      n = (int)(c.reading_filters.size() + c.reading_step_filters.size() + c.reference_filters.size() +
+                c.outlier_filters.size() + c.checkers.size()) + 4;
+    } else {
+      n = (int)module_list_from_yaml(Kind::DataPointsFilter, parse_yaml(std::string(yaml, len))).size();
+    }
+    if (n_modules) *n_modules = n;
+  } catch (const pgs::Error& ex) {
+    code = ex.code;
+    msg = ex.what();
+  } catch (const std::exception& ex) {
+    code = PGS_INVALID_ARGUMENT;
+    msg = ex.what();
+  }
+  if (err && cap > 0) {
+    std::strncpy(err, msg.c_str(), cap - 1);
+    err[cap - 1] = '\0';
+  }
+  return (pgs_status)code;
+}
+
+int pgs_registrar_count(int kind) {
+  if (kind < 0 || kind > 7) return 0;
+  return (int)registered_modules((Kind)kind).size();
+}
+
+const char* pgs_registrar_name(int kind, int index) {
+  static thread_local std::string name;
+  if (kind < 0 || kind > 7) return "";
+  auto v = registered_modules((Kind)kind);
+  if (index < 0 || index >= (int)v.size()) return "";
+  name = v[index];
+  return name.c_str();
+}
+
 uint64_t pgs_ctx_launch_count(const pgs_ctx* ctx) { return ctx->c.launches; }
 
 pgs_status pgs_ctx_set_profiling(pgs_ctx* ctx, int enabled) {

@@ -390,16 +390,11 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   float3 q = xform_rn(T, r.x, r.y, r.z);
   Best1 acc;
   acc.init();
-  if (st.iterations > 0) {
-    // temporal coherence: last iteration's match is an excellent first bound
-    int pp = v.match_pos[i];
-    if (pp >= 0) {
-      float4 c = v.tree.pts[pp];
-      float d = dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
-      if (d <= maxr2) acc.offer(d, __float_as_int(c.w), pp);
-    }
-  }
-  knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
+  // temporal coherence: after the first iteration the previous match is almost
+  // always still the answer, so search bottom-up from its leaf
+  const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
+  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, maxr2, acc);
+  else knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
   v.match_pos[i] = acc.pos;
   v.match_d2[i] = acc.d;
 }

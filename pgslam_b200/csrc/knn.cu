@@ -30,19 +30,20 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   const float4 q = job.queries[j];
   BestK<K> acc;
   acc.init();
-  int skip_lo = 0, skip_hi = -1;
   if (job.self) {
     // neighbours in Morton order are mostly neighbours in space: they give a
-    // tight k-th distance before the tree is touched, so the walk prunes hard
-    skip_lo = max(0, j - K);
-    skip_hi = min(job.tree.n - 1, j + K);
+    // tight k-th distance before the tree is touched, so the climb from the
+    // query's own leaf enters almost no sibling subtree
+    const int skip_lo = max(0, j - K), skip_hi = min(job.tree.n - 1, j + K);
     for (int p = skip_lo; p <= skip_hi; ++p) {
       float4 c = job.tree.pts[p];
       float dd = dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
       if (dd <= maxr2) acc.offer(dd, __float_as_int(c.w), p);
     }
+    knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, maxr2, acc, skip_lo, skip_hi);
+  } else {
+    knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc);
   }
-  knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc, skip_lo, skip_hi);
   const int col = job.qperm ? job.qperm[j] : j;
   int32_t* oi = job.ids + (size_t)col * k;
   float* od = job.d2 + (size_t)col * k;

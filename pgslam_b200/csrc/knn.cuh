@@ -71,14 +71,29 @@ struct BestK {
   }
 };
 
-// skip_lo..skip_hi: sorted positions already offered by the caller (self-kNN
-// window seeding); pass an empty range (0, -1) otherwise.
 template <class Acc>
-__device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz, float maxr2,
-                                             Acc& acc, int skip_lo = 0, int skip_hi = -1) {
+__device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float qx, float qy, float qz, float maxr2,
+                                              Acc& acc, int skip_lo, int skip_hi) {
+  if (leaf >= t.n_leaves) return;
+  const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
+  const int base = leaf * kLeaf;
+#pragma unroll
+  for (int j = 0; j < kLeaf; ++j) {
+    float4 p = lp[j];
+    float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+    const int pos = base + j;
+    if (dd <= maxr2 && (pos < skip_lo || pos > skip_hi)) acc.offer(dd, __float_as_int(p.w), pos);
+  }
+}
+
+// Exhaustive best-first walk of the subtree under `node` (at `depth`), whose own
+// box the caller has already accepted.  skip_lo..skip_hi: sorted positions the
+// caller has already offered (pass an empty range (0, -1) otherwise).
+template <class Acc>
+__device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned node, int depth, float qx, float qy,
+                                                  float qz, float maxr2, Acc& acc, int skip_lo, int skip_hi) {
   const float4* __restrict__ nodes4 = reinterpret_cast<const float4*>(t.nodes);
-  unsigned node = 1, trail = 0;
-  int depth = 0;
+  unsigned trail = 0;
   while (true) {
     // ---- descend while the nearer child qualifies -------------------------
     bool at_leaf = true;
@@ -95,21 +110,7 @@ __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float 
       node = node * 2 + (near1 ? 1u : 0u);
       ++depth;
     }
-    // ---- leaf ----------------------------------------------------------------
-    if (at_leaf) {
-      const int leaf = (int)node - t.P;
-      if (leaf < t.n_leaves) {
-        const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
-        const int base = leaf * kLeaf;
-#pragma unroll
-        for (int j = 0; j < kLeaf; ++j) {
-          float4 p = lp[j];
-          float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-          const int pos = base + j;
-          if (dd <= maxr2 && (pos < skip_lo || pos > skip_hi)) acc.offer(dd, __float_as_int(p.w), pos);
-        }
-      }
-    }
+    if (at_leaf) knn_scan_leaf(t, (int)node - t.P, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
     // ---- walk back to the deepest pending sibling whose box still qualifies --
     while (true) {
       if (trail == 0) return;
@@ -123,6 +124,52 @@ __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float 
       float lb = box_lb_rn(qx, qy, qz, nb[0], nb[1], nb[2], nb[3], nb[4], nb[5]);
       if (lb <= fminf(acc.bound(), maxr2)) break;
     }
+  }
+}
+
+// top-down search from the root (no prior knowledge about the query)
+template <class Acc>
+__device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz, float maxr2,
+                                             Acc& acc, int skip_lo = 0, int skip_hi = -1) {
+  knn_traverse_from(t, 1u, 0, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+}
+
+// Bottom-up search from a seed leaf (last iteration's match, or the query's own
+// leaf for self-kNN): scan the leaf, then climb to the root testing the SIBLING
+// subtree at every level.  The sibling boxes sit at addresses known from the
+// leaf index alone, so their loads are independent (four levels in flight at a
+// time) instead of the root descent's chain of dependent loads; with a tight
+// seed almost every sibling fails its bound test and is never entered.  The
+// union of the seed leaf and all sibling subtrees is the whole tree, so the
+// result is the same exact minimum as the top-down walk.
+template <class Acc>
+__device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx, float qy, float qz, float maxr2,
+                                          Acc& acc, int skip_lo = 0, int skip_hi = -1) {
+  knn_scan_leaf(t, leaf, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+  unsigned node = (unsigned)(t.P + leaf);
+  int depth = t.depth;
+  const float inf = __int_as_float(0x7f800000);
+  while (depth > 0) {
+    float lbv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lbv[u] = inf;
+      if (depth - u > 0) {
+        const unsigned sib = (node >> u) ^ 1u;
+        const float2* __restrict__ nb = reinterpret_cast<const float2*>(t.nodes + (size_t)sib * 6);
+        float2 a = nb[0], b = nb[1], c = nb[2];
+        lbv[u] = box_lb_rn(qx, qy, qz, a.x, a.y, b.x, b.y, c.x, c.y);
+      }
+    }
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+      const float lb = u == 0 ? lbv[0] : (u == 1 ? lbv[1] : (u == 2 ? lbv[2] : lbv[3]));
+      // an empty box has lb = +inf: the `< inf` test keeps an unbounded first search out of it
+      if (lb < inf && lb <= fminf(acc.bound(), maxr2))
+        knn_traverse_from(t, (node >> u) ^ 1u, depth - u, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+    }
+    node >>= 4;
+    depth -= 4;
   }
 }
 

@@ -123,6 +123,9 @@ SIGNATURES = {
     "pgs_icp_run_batch": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _dp, C.POINTER(IcpResult)]),
     "pgs_icp_probe_overlap": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "pgs_icp_probe_residual": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
+    "pgs_config_check": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "pgs_registrar_count": (C.c_int, [C.c_int]),
+    "pgs_registrar_name": (C.c_char_p, [C.c_int, C.c_int]),
     "pgs_ctx_launch_count": (C.c_uint64, [_vp]),
     "pgs_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "pgs_ctx_last_stage_times": (C.c_int, [_vp, C.POINTER(StageTimes)]),
@@ -144,6 +147,30 @@ def load_library():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+KINDS = ("DataPointsFilter", "Matcher", "OutlierFilter", "ErrorMinimizer", "TransformationChecker", "Inspector",
+         "Logger", "Transformation")
+
+
+def check_config(yaml_text: str, chain: bool = True) -> int:
+    """Parse + validate a libpointmatcher YAML on the host (no GPU needed).
+    Returns the number of modules; raises the PointMatcher-style exception otherwise."""
+    L = load_library()
+    b = yaml_text.encode()
+    n = C.c_int(0)
+    err = C.create_string_buffer(512)
+    st = L.pgs_config_check(b, len(b), int(chain), C.byref(n), err, 512)
+    if st != OK:
+        raise _EXC.get(st, PointMatcherError)(st, err.value.decode())
+    return n.value
+
+
+def registered(kind: str) -> list[str]:
+    """PM::get().REG(kind): the names of the registered modules."""
+    L = load_library()
+    k = KINDS.index(kind)
+    return [L.pgs_registrar_name(k, i).decode() for i in range(L.pgs_registrar_count(k))]
 
 
 def _mat(T):

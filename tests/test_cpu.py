@@ -1,0 +1,350 @@
+"""CPU suite (`-m "not gpu"`): pins the oracle (golden vectors + independent
+cross-checks), exercises the host logic of the library (YAML / registrar /
+parameter validation, no device needed), checks that the C-ABI library loads and
+exports every symbol include/pgslam_b200.h declares, and covers the N > 1
+sharding path with a world_size-2 gloo run."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from pgslam_b200 import build, dist as pdist, pm, synth
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "pair4000.npz"))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build.build()
+    ob.build()
+
+
+# ------------------------------------------------------------ C ABI surface ---
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pgslam_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pgs_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 55
+    out = subprocess.run(["nm", "-D", "--defined-only", pm.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (pgs_[a-z0-9_]+)", out))
+    assert declared <= exported, sorted(declared - exported)
+    assert declared == set(pm.SIGNATURES), sorted(declared ^ set(pm.SIGNATURES))
+    L = pm.load_library()
+    assert b"sm_100a" in L.pgs_version()
+
+
+def test_no_silent_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pm.CudaError, match="no CPU fallback"):
+        pm.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pgslam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.replace("the CPU oracle", "").replace("CPU oracle", "") or f == "synth.py", f
+
+
+# ----------------------------------------------------- host logic: YAML/registrar ---
+def test_config_check_accepts_the_baseline_chains():
+    for cfg in (util.C1, util.C2, util.C2_COV, util.C5):
+        assert pm.check_config(util.to_yaml(cfg)) >= 5
+    assert pm.check_config(util.to_yaml(util.INPUT_FILTERS), chain=False) == 4
+    assert pm.check_config("", chain=False) == 0
+
+
+def test_config_check_block_and_flow_yaml_styles():
+    block = """
+# comment
+readingDataPointsFilters:
+  - RandomSamplingDataPointsFilter:
+      prob: 0.5
+referenceDataPointsFilters:
+  - SurfaceNormalDataPointsFilter: {knn: 10, epsilon: 0}   # flow map
+matcher:
+  KDTreeMatcher:
+    knn: 1
+    epsilon: 0
+outlierFilters:
+- TrimmedDistOutlierFilter:
+    ratio: 0.75
+errorMinimizer:
+  PointToPlaneErrorMinimizer
+transformationCheckers:
+  - CounterTransformationChecker: {maxIterationCount: 40}
+  - DifferentialTransformationChecker:
+      minDiffRotErr: 0.001
+      minDiffTransErr: 0.01
+      smoothLength: 4
+inspector: NullInspector
+logger: NullLogger
+"""
+    assert pm.check_config(block) == 9
+    assert pm.check_config("readingStepDataPointsFilters: []\nmatcher: KDTreeMatcher\n") == 4
+
+
+@pytest.mark.parametrize("text,exc", [
+    ("matcher:\n  KDTreeMatcher:\n    knn: 0\n", pm.InvalidParameter),
+    ("matcher:\n  KDTreeMatcher: {bogus: 1}\n", pm.InvalidParameter),
+    ("matcher:\n  KDTreeMatcher: {knn: abc}\n", pm.InvalidParameter),
+    ("outlierFilters:\n  - TrimmedDistOutlierFilter: {ratio: 2}\n", pm.InvalidParameter),
+    ("matcher: NoSuchMatcher\n", pm.InvalidElement),
+    ("somethingElse:\n  - X\n", pm.InvalidModuleType),
+    ("matcher:\n  KDTreeMatcher: {knn: 3}\n", pm.InvalidParameter),  # fused loop is k = 1
+    ("errorMinimizer:\n  PointToPlaneErrorMinimizer: {force2D: 1}\n", pm.InvalidParameter),
+])
+def test_config_check_rejects_like_libpointmatcher(text, exc):
+    with pytest.raises(exc):
+        pm.check_config(text)
+
+
+def test_registrar_lists_the_modules_the_path_needs():
+    assert {"RandomSamplingDataPointsFilter", "VoxelGridDataPointsFilter", "SurfaceNormalDataPointsFilter",
+            "ObservationDirectionDataPointsFilter", "OrientNormalsDataPointsFilter",
+            "SimpleSensorNoiseDataPointsFilter"} <= set(pm.registered("DataPointsFilter"))
+    assert pm.registered("Matcher") == ["KDTreeMatcher"]
+    assert "TrimmedDistOutlierFilter" in pm.registered("OutlierFilter")
+    assert {"PointToPlaneErrorMinimizer", "PointToPlaneWithCovErrorMinimizer", "PointToPointErrorMinimizer"} <= set(
+        pm.registered("ErrorMinimizer"))
+    assert {"CounterTransformationChecker", "DifferentialTransformationChecker", "BoundTransformationChecker"} == set(
+        pm.registered("TransformationChecker"))
+    assert pm.registered("Transformation") == ["RigidTransformation"]
+
+
+# ------------------------------------------------------- oracle vs golden vectors ---
+def test_oracle_knn_matches_golden():
+    rd, rf = GOLD["reading"], GOLD["reference"]
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    assert np.array_equal(ids, GOLD["knn1_ids"]) and np.array_equal(d2, GOLD["knn1_d2"])
+    ids, d2 = ob.kdtree_knn(rf, rf, k=5)
+    assert np.array_equal(ids, GOLD["knn5_ids"]) and np.array_equal(d2, GOLD["knn5_d2"])
+
+
+def test_oracle_filters_match_golden():
+    oc = ob.Cloud(GOLD["reference"])
+    ob.apply_filter(oc, "SurfaceNormalDataPointsFilter", knn=10, keepDensities=1, keepEigenValues=1)
+    assert np.array_equal(oc.desc("normals"), GOLD["normals"])
+    assert np.array_equal(oc.desc("dens"), GOLD["densities"])
+    assert np.array_equal(oc.desc("eigval"), GOLD["eigvalues"])
+    vox = ob.Cloud(GOLD["reading"])
+    ob.apply_filter(vox, "VoxelGridDataPointsFilter", vSizeX=0.5, vSizeY=0.5, vSizeZ=0.5)
+    assert np.array_equal(vox.features, GOLD["voxel_features"])
+    st, w = ob.outlier_weights([{"TrimmedDistOutlierFilter": {"ratio": 0.85}}], GOLD["knn1_d2"])
+    assert st == 0 and np.array_equal(w, GOLD["trimmed_weights"])
+
+
+@pytest.mark.parametrize("name,cfg", [("c1", util.C1), ("c2", util.C2), ("c2cov", util.C2_COV)])
+def test_oracle_icp_matches_golden(name, cfg):
+    r = ob.icp_run(cfg, ob.Cloud(GOLD["reading"]), ob.Cloud(GOLD["reference"]))
+    assert r["status"] == 0 and r["iterations"] == int(GOLD[name + "_iterations"])
+    np.testing.assert_allclose(r["T"], GOLD[name + "_T"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(r["cov"], GOLD[name + "_cov"], rtol=1e-9, atol=1e-20)
+    assert r["residual"] == pytest.approx(float(GOLD[name + "_residual"]), rel=1e-10)
+
+
+# ------------------------------------------ oracle pinned by independent methods ---
+def test_oracle_kdtree_equals_brute_force_twin():
+    rd, rf, _ = synth.scan_pair(7, beams=16, az_steps=400)
+    for k in (1, 4, 10):
+        a = ob.kdtree_knn(rf, rd, k=k)
+        b = ob.brute_knn(rf, rd, k=k)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    a = ob.kdtree_knn(rf, rd, k=3, max_dist=0.3)
+    b = ob.brute_knn(rf, rd, k=3, max_dist=0.3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (a[0] == -1).any() and np.isinf(a[1][a[0] == -1]).all()
+
+
+def test_oracle_knn_agrees_with_scipy_ckdtree():
+    from scipy.spatial import cKDTree
+    rd, rf, _ = synth.scan_pair(8, beams=16, az_steps=400)
+    ids, d2 = ob.kdtree_knn(rf, rd, k=2)
+    dd, ii = cKDTree(rf[:3].T.astype(np.float64)).query(rd[:3].T.astype(np.float64), k=2)
+    clear = (dd[:, 1] - dd[:, 0]) > 1e-4  # away from fp32 near-ties
+    assert clear.mean() > 0.9
+    assert np.array_equal(ids[0][clear], ii[:, 0][clear])
+    np.testing.assert_allclose(np.sqrt(d2[0][clear]), dd[:, 0][clear], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_ties_go_to_the_lower_index():
+    base = np.random.default_rng(0).uniform(-3, 3, size=(3, 200)).astype(np.float32)
+    ref = np.ones((4, 600), np.float32)
+    ref[:3] = np.concatenate([base, base, base], axis=1)
+    ids, d2 = ob.kdtree_knn(ref, ref, k=3)
+    assert np.array_equal(ids[0], np.arange(600) % 200)
+    assert np.array_equal(ids[1], np.arange(600) % 200 + 200)
+    assert (d2 == 0).all()
+
+
+def test_oracle_quantile_is_the_exact_order_statistic():
+    g = np.random.default_rng(1)
+    d = g.gamma(2.0, 0.01, size=5000).astype(np.float32)
+    d[:40] = 0.0
+    d[40:50] = np.inf
+    vals = np.sort(d[(d > 0) & np.isfinite(d)])
+    for q in (0.5, 0.75, 0.85, 0.999, 1.0):
+        st, w = ob.outlier_weights([{"TrimmedDistOutlierFilter": {"ratio": q}}], d[None])
+        limit = vals[-1] if q == 1.0 else vals[int(len(vals) * q)]
+        assert st == 0 and np.array_equal(w[0], (d <= limit).astype(np.float32))
+    st, _ = ob.outlier_weights([{"TrimmedDistOutlierFilter": {"ratio": 0.85}}], np.zeros((1, 10), np.float32))
+    assert st == ob.CONVERGENCE_ERROR
+
+
+def test_oracle_dense_algebra_against_numpy():
+    import ctypes as C
+    L = ob.lib()
+    g = np.random.default_rng(2)
+    for _ in range(50):
+        M = g.normal(size=(3, 3))
+        A = np.asfortranarray(M @ M.T)
+        w, V = np.zeros(3), np.zeros((3, 3), order="F")
+        L.orc_eig3_sym(ob._d(A), ob._d(w), ob._d(V))
+        np.testing.assert_allclose(np.sort(w), np.linalg.eigvalsh(A), rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(A @ V, V * w, atol=1e-12)
+        G = g.normal(size=(6, 6))
+        H = np.asfortranarray(G @ G.T + 0.1 * np.eye(6))
+        b, x = g.normal(size=6), np.zeros(6)
+        assert L.orc_solve6(ob._d(H), ob._d(b), ob._d(x)) == 6
+        np.testing.assert_allclose(x, np.linalg.solve(H, b), rtol=1e-9)
+        U, S, Vt = np.zeros((3, 3), order="F"), np.zeros(3), np.zeros((3, 3), order="F")
+        Mf = np.asfortranarray(M)
+        L.orc_svd3(ob._d(Mf), ob._d(U), ob._d(S), ob._d(Vt))
+        np.testing.assert_allclose(S, np.linalg.svd(M, compute_uv=False), rtol=1e-7)
+        np.testing.assert_allclose(U @ np.diag(S) @ Vt.T, M, atol=1e-8)
+    # rank-deficient normal equations take the minimum-norm branch
+    H = np.zeros((6, 6), order="F")
+    H[:3, :3] = np.eye(3)
+    b, x = np.array([1.0, 2, 3, 0, 0, 0]), np.zeros(6)
+    assert L.orc_solve6(ob._d(H), ob._d(b), ob._d(x)) == 3
+    np.testing.assert_allclose(x, np.linalg.pinv(H) @ b, atol=1e-12)
+
+
+@pytest.mark.parametrize("minimizer", ["PointToPointErrorMinimizer", "PointToPlaneErrorMinimizer"])
+def test_oracle_icp_recovers_a_known_rigid_motion(minimizer):
+    # noiseless box room sampled uniformly on its faces (no ray pattern to alias on)
+    g = np.random.default_rng(9)
+    n = 4000
+    faces = []
+    for axis, val in ((0, -5.0), (0, 5.0), (1, -4.0), (1, 4.0), (2, 0.0), (2, 3.0)):
+        p = np.stack([g.uniform(-5, 5, n), g.uniform(-4, 4, n), g.uniform(0, 3, n)])
+        p[axis] = val
+        faces.append(p)
+    rf = np.ones((4, 6 * n), np.float32)
+    rf[:3] = np.concatenate(faces, axis=1).astype(np.float32)
+    T = synth.pose_matrix([0.15, -0.1, 0.04], 0.03, 0.01, -0.015)
+    rd = (np.linalg.inv(T) @ rf.astype(np.float64)).astype(np.float32)
+    cfg = dict(util.C2, errorMinimizer=minimizer,
+               outlierFilters=[{"TrimmedDistOutlierFilter": {"ratio": 0.95}}],
+               transformationCheckers=[{"CounterTransformationChecker": {"maxIterationCount": 400}},
+                                       {"DifferentialTransformationChecker": {"minDiffRotErr": 1e-7,
+                                                                              "minDiffTransErr": 1e-7}}])
+    r = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf))
+    assert r["status"] == 0 and not r["max_iter_reached"]
+    np.testing.assert_allclose(r["T"], T, atol=1e-5)
+
+
+def test_oracle_icp_is_equivariant_under_a_common_rigid_motion():
+    rd, rf, _ = synth.scan_pair(10, beams=16, az_steps=300)
+    G = synth.pose_matrix([1.0, -2.0, 0.3], 0.4, 0.0, 0.0)
+    base = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))
+    rf2 = (G @ rf.astype(np.float64)).astype(np.float32)
+    moved = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf2), G)
+    assert base["status"] == moved["status"] == 0
+    np.testing.assert_allclose(moved["T"], G @ base["T"], atol=5e-3)  # fp32 clouds, different roundings
+
+
+def test_oracle_sequence_matches_full_icp_up_to_filter_order():
+    rd, rf, _ = synth.scan_pair(12, beams=16, az_steps=300)
+    seq = ob.IcpSequence(util.C1)  # no reference filters: setMap order is irrelevant
+    assert seq.set_map(ob.Cloud(rf)) == 0
+    a = seq.run(ob.Cloud(rd))
+    b = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))
+    assert a["iterations"] == b["iterations"]
+    np.testing.assert_array_equal(a["T"], b["T"])
+
+
+def test_oracle_error_paths():
+    rd, rf, _ = synth.scan_pair(13, beams=16, az_steps=100)
+    r = ob.icp_run(dict(util.C2, referenceDataPointsFilters=[]), ob.Cloud(rd), ob.Cloud(rf))
+    assert r["status"] == ob.INVALID_FIELD
+    bad = np.eye(4)
+    bad[0, 0] = 2
+    assert ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf), bad)["status"] == ob.TRANSFORMATION_ERROR
+    c = ob.Cloud(rd)
+    assert ob.apply_filter(c, "OrientNormalsDataPointsFilter") == ob.INVALID_FIELD
+
+
+def test_synth_scans_are_exact_size_and_reproducible():
+    a = synth.scan_pair(3, beams=16, az_steps=64)
+    b = synth.scan_pair(3, beams=16, az_steps=64)
+    assert a[0].shape == (4, 1024) and a[0].dtype == np.float32
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    r = np.linalg.norm(a[0][:3], axis=0)
+    assert r.min() >= 0.99 and r.max() <= 80.01 and np.all(a[0][3] == 1.0)
+
+
+# ---------------------------------------------------------- N > 1: gloo, 2 ranks ---
+def test_shard_ranges_partition_the_pairs():
+    for P, G in ((4096, 8), (10, 4), (3, 8), (0, 2)):
+        seen = [i for r in range(G) for i in pdist.shard_range(P, r, G)]
+        assert seen == list(range(P))
+
+
+def test_result_packing_roundtrip():
+    res = [dict(T=np.arange(16.0).reshape(4, 4), covariance=np.eye(6) * i, iterations=i, status=0,
+                max_iterations_reached=bool(i % 2), overlap=0.5, residual=1.5, weighted_point_used_ratio=0.85)
+           for i in range(3)]
+    back = pdist.unpack_results(pdist.pack_results(res))
+    for a, b in zip(res, back):
+        assert np.array_equal(a["T"], b["T"]) and np.array_equal(a["covariance"], b["covariance"])
+        assert a["iterations"] == b["iterations"] and a["max_iterations_reached"] == b["max_iterations_reached"]
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from pgslam_b200 import dist as pdist, synth
+from oracle import binding as ob
+from tests import util
+dist.init_process_group("gloo")
+pairs = [synth.scan_pair(s, beams=16, az_steps=60)[:2] for s in range(5)]
+def run(block):   # the CPU stand-in for ICP.compute_batch in this CPU-only test
+    out = []
+    for rd, rf in block:
+        r = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))
+        out.append(dict(T=r["T"], covariance=r["cov"], iterations=r["iterations"], status=r["status"],
+                        max_iterations_reached=r["max_iter_reached"], overlap=r["overlap"], residual=r["residual"],
+                        weighted_point_used_ratio=r["weighted_ratio"]))
+    return out
+res = pdist.register_sharded(run, pairs)
+np.save(os.path.join(sys.argv[2], f"rank{dist.get_rank()}.npy"), pdist.pack_results(res))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding_gives_the_unsharded_results(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT, str(tmp_path)],
+                   check=True, env=env, timeout=300, capture_output=True)
+    a, b = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
+    assert np.array_equal(a, b) and a.shape == (5, pdist.RESULT_WIDTH)
+    for i in range(5):
+        rd, rf = synth.scan_pair(i, beams=16, az_steps=60)[:2]
+        want = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))
+        assert np.array_equal(a[i, :16].reshape(4, 4).T, want["T"])  # independent of the sharding
+        assert int(a[i, 52]) == want["iterations"]

@@ -441,3 +441,79 @@ def test_assemble_local_map(pm, pair30k):
     assert out.getNbPoints() == rf.shape[1] + rd.shape[1]
     assert np.array_equal(out.features[:, :rf.shape[1]], rf)
     assert np.array_equal(out.features[:, rf.shape[1]:].view(np.uint32), oc.features.view(np.uint32))
+
+
+# ------------------------------------------------ committed golden vectors (tests/golden) ---
+def test_gpu_against_committed_golden_vectors(pm):
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pair4000.npz"))
+    rd, rf = G["reading"], G["reference"]
+    m = pm.Matcher("KDTreeMatcher", {"knn": 1})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd))
+    assert np.array_equal(got.ids, G["knn1_ids"]) and np.array_equal(got.dists, G["knn1_d2"])
+    m5 = pm.Matcher("KDTreeMatcher", {"knn": 5})
+    m5.init(pm.DataPoints(rf))
+    got = m5.findClosests(pm.DataPoints(rf))
+    assert np.array_equal(got.ids, G["knn5_ids"]) and np.array_equal(got.dists, G["knn5_d2"])
+    dp = pm.DataPoints(rf)
+    f = pm.DataPointsFilters()
+    f.append("SurfaceNormalDataPointsFilter", {"knn": 10, "keepDensities": 1, "keepEigenValues": 1})
+    f.apply(dp)
+    assert np.array_equal(dp.getDescriptorByName("normals"), G["normals"])
+    assert np.array_equal(dp.getDescriptorByName("densities"), G["densities"])
+    assert np.array_equal(dp.getDescriptorByName("eigValues"), G["eigvalues"])
+    vox = pm.DataPoints(rd)
+    f = pm.DataPointsFilters()
+    f.append("VoxelGridDataPointsFilter", {"vSizeX": 0.5, "vSizeY": 0.5, "vSizeZ": 0.5})
+    f.apply(vox)
+    assert np.array_equal(vox.features, G["voxel_features"])
+    o = pm.OutlierFilters()
+    o.append("TrimmedDistOutlierFilter", {"ratio": 0.85})
+    w = o.compute(pm.DataPoints(rd), pm.DataPoints(rf), pm.Matches(G["knn1_ids"], G["knn1_d2"]))
+    assert np.array_equal(w, G["trimmed_weights"])
+    for name, cfg in (("c1", util.C1), ("c2", util.C2), ("c2cov", util.C2_COV)):
+        icp = pm.ICP()
+        icp.loadFromYaml(util.to_yaml(cfg))
+        T = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+        assert icp.last["iterations"] == int(G[name + "_iterations"])
+        util.assert_pose_close(T, G[name + "_T"])
+        if name == "c2cov":
+            np.testing.assert_allclose(icp.errorMinimizer.getCovariance(), G[name + "_cov"], rtol=1e-6, atol=1e-18)
+
+
+def test_full_size_properties_120k(pm, pair120k):
+    """Size-independent properties at BASELINE.json's full size."""
+    rd, rf, truth = pair120k
+    # (1) self-kNN: every point is its own nearest neighbour at distance 0 and the list is sorted
+    m = pm.Matcher("KDTreeMatcher", {"knn": 4})
+    ref = pm.DataPoints(rf)
+    m.init(ref)
+    got = m.findClosests(ref)
+    assert np.array_equal(got.ids[0], np.arange(rf.shape[1])) and (got.dists[0] == 0).all()
+    assert (np.diff(got.dists, axis=0) >= 0).all()
+    # (2) kNN is invariant to a permutation of the reference (ids map through the permutation)
+    perm = np.random.default_rng(0).permutation(rf.shape[1])
+    m1 = pm.Matcher("KDTreeMatcher", {"knn": 1})
+    m1.init(ref)
+    a = m1.findClosests(pm.DataPoints(rd))
+    m1.init(pm.DataPoints(rf[:, perm]))
+    b = m1.findClosests(pm.DataPoints(rd))
+    assert np.array_equal(a.dists, b.dists)
+    same = perm[b.ids[0]] == a.ids[0]
+    assert same.mean() > 0.9999  # only exact-distance ties may resolve to another index
+    # (3) trimmed weights keep exactly the requested fraction of the valid matches
+    o = pm.OutlierFilters()
+    o.append("TrimmedDistOutlierFilter", {"ratio": 0.85})
+    w = o.compute(pm.DataPoints(rd), ref, a)
+    valid = (a.dists > 0) & np.isfinite(a.dists)
+    assert abs(w[valid].mean() - 0.85) < 2e-5
+    # (4) registering a cloud against a rigidly moved copy of itself returns the motion
+    T = synth.pose_matrix([0.1, -0.05, 0.02], 0.01, 0.002, -0.003)
+    moved = (np.linalg.inv(T) @ rf.astype(np.float64)).astype(np.float32)
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(dict(util.C2, transformationCheckers=[
+        {"CounterTransformationChecker": {"maxIterationCount": 60}},
+        {"DifferentialTransformationChecker": {"minDiffRotErr": 1e-6, "minDiffTransErr": 1e-6}}])))
+    out = icp(pm.DataPoints(moved), ref)
+    np.testing.assert_allclose(out, T, atol=2e-5)
