@@ -78,6 +78,8 @@ void Cloud::remove(const std::string& label) {
 std::unique_ptr<Cloud> Cloud::clone() const {
   auto c = std::make_unique<Cloud>(ctx);
   c->n = n;
+  c->kd_order = kd_order;  // same points, same order
+  c->kd_order_n = kd_order_n;
   c->feat.reset(ctx, (size_t)n);
   if (n) PGS_CUDA(cudaMemcpyAsync(c->feat.p, feat.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   for (auto& d : descs) {
@@ -95,6 +97,7 @@ std::unique_ptr<Cloud> Cloud::clone() const {
 // in both clouds with equal span.
 void concatenate_cloud(Cloud& a, const Cloud& b) {
   Ctx* ctx = a.ctx;
+  a.touch();
   const int64_t na = a.n, nb = b.n;
   DBuf<float4> nf(ctx, (size_t)(na + nb));
   if (na) PGS_CUDA(cudaMemcpyAsync(nf.p, a.feat.p, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -29,6 +29,11 @@ struct Cloud {
   int64_t n = 0;
   DBuf<float4> feat;
   std::vector<Desc> descs;
+  // kd order of `feat` (index.cu), valid while the points are untouched; every
+  // function that moves, adds or removes points calls touch()
+  std::shared_ptr<DBuf<uint32_t>> kd_order;
+  int64_t kd_order_n = -1;
+  void touch() { kd_order.reset(); kd_order_n = -1; }
 
   explicit Cloud(Ctx* c) : ctx(c) {}
   Desc* find(const std::string& label) {
@@ -93,9 +98,15 @@ struct Index {
 // job b's points are translated by -shift[b] (fp32 subtraction, the
 // mean-centring of ICP::compute) before being stored; boxes are built from the
 // stored coordinates.
+enum class IndexOrder { Kd, Morton };
 void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std::vector<int>& n,
                    const float* d_shift /* 4 floats per job or nullptr */,
-                   std::vector<std::unique_ptr<Index>>& out);
+                   std::vector<std::unique_ptr<Index>>& out, IndexOrder order_kind = IndexOrder::Kd,
+                   const std::vector<const uint32_t*>* given_order = nullptr,
+                   std::vector<DBuf<uint32_t>>* keep_order = nullptr);
+// same for clouds; caches / reuses the kd order in the Cloud objects
+void build_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, const float* d_shift,
+                              std::vector<std::unique_ptr<Index>>& out);
 
 // ---------------------------------------------------------------------------
 // exact kNN (eps = 0, ties -> lower original index), k <= 32.

@@ -300,6 +300,7 @@ voxel_reduce_kernel(float4* __restrict__ feat, const uint64_t* __restrict__ keys
 void voxel_grid(Ctx* ctx, const Module& m, Cloud& c) {
   const int n = (int)c.n;
   if (n == 0) return;
+  c.touch();
   cudaStream_t s = ctx->stream;
   DBuf<unsigned> bb(ctx, 6);
   DBuf<float> bbf(ctx, 6);
@@ -360,11 +361,10 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
     throw Error(PGS_INVALID_PARAMETER,
                 "SurfaceNormalDataPointsFilter: keepMatchedIds/keepMeanDist/sortEigen/smoothNormals are not supported");
   const int B = (int)clouds.size();
-  std::vector<const float4*> pts(B);
   std::vector<int> ns(B);
-  for (int b = 0; b < B; ++b) { pts[b] = clouds[b]->feat.p; ns[b] = (int)clouds[b]->n; }
+  for (int b = 0; b < B; ++b) ns[b] = (int)clouds[b]->n;
   std::vector<std::unique_ptr<Index>> idx;
-  build_indices(ctx, pts, ns, nullptr, idx);
+  build_indices_for_clouds(ctx, clouds, nullptr, idx);
   std::vector<DBuf<int32_t>> ids(B);
   std::vector<DBuf<float>> d2(B);
   std::vector<const Index*> ip(B);
@@ -419,6 +419,7 @@ Xf xf_from_T(const double* T) {
 void rigid_transform_cloud(Cloud& c, const double* T) {
   if (!is_rigid(T)) throw Error(PGS_TRANSFORMATION_ERROR, "RigidTransformation: Error, rotation matrix is not orthogonal.");
   if (c.n == 0) return;
+  c.touch();
   Desc* nrm = c.find("normals");
   Desc* obs = c.find("observationDirections");
   rigid_kernel<<<ceil_div(c.n, 256), 256, 0, c.ctx->stream>>>(c.feat.p, nrm ? nrm->data.p : nullptr,

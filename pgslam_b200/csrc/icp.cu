@@ -970,6 +970,7 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     compute_mean();
     for (int b = 0; b < B; ++b)
       if (rp[b]->n) {
+        rp[b]->touch();
         shift_points_kernel<<<ceil_div(rp[b]->n, 256), 256, 0, s>>>(rp[b]->feat.p, (int)rp[b]->n, shift.p + 4 * b);
         ctx_count_launches(ctx, 1);
       }
@@ -979,11 +980,12 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     apply_filters(ctx, cfg_.reference_filters, rp);
     compute_mean();
   }
-  std::vector<const float4*> pts(B);
   std::vector<int> ns(B);
-  for (int b = 0; b < B; ++b) { pts[b] = rp[b]->feat.p; ns[b] = (int)rp[b]->n; }
+  for (int b = 0; b < B; ++b) ns[b] = (int)rp[b]->n;
   std::vector<std::unique_ptr<Index>> idx;
-  build_indices(ctx, pts, ns, centre_first ? nullptr : shift.p, idx);
+  // the kd order is translation invariant: if the SurfaceNormal filter already
+  // built it for this (unchanged) cloud it is reused here
+  build_indices_for_clouds(ctx, rp, centre_first ? nullptr : shift.p, idx);
   std::vector<double> hT((size_t)16 * B);
   Tmean.download(hT.data(), hT.size());
   out.clear();
@@ -1100,6 +1102,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     if (max_nr > 0) {
       DBuf<PreJob> d_pj(ctx, P);
       ctx->upload_small(d_pj.p, pj.data(), sizeof(PreJob) * P);
+      for (int p = 0; p < P; ++p) rdp[p]->touch();
       pretransform_kernel<<<dim3(ceil_div(max_nr, 256), P), 256, 0, s>>>(d_pj.p, d_states.p);
       ctx_count_launches(ctx, 1);
     }
@@ -1109,7 +1112,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     std::vector<const float4*> pts(P);
     std::vector<int> ns(P);
     for (int p = 0; p < P; ++p) { pts[p] = rdp[p]->feat.p; ns[p] = (int)rdp[p]->n; }
-    build_indices(ctx, pts, ns, nullptr, rd_sorted);
+    build_indices(ctx, pts, ns, nullptr, rd_sorted, IndexOrder::Morton);
   }
 
   // ---- per-pair views ----------------------------------------------------------

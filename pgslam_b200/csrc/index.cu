@@ -21,6 +21,7 @@ struct BuildJob {
   float4* dst;    // sorted points (n_leaves * kLeaf entries)
   float* nodes;   // 2*P*6 floats
   int n, n_leaves, P, depth;
+  const uint32_t* order;  // order[j] = original index of the j-th point in tree order
 };
 
 __global__ void bbox_init_kernel(unsigned* bbox, int n_jobs) {
@@ -94,8 +95,7 @@ morton_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift
 }
 
 __global__ void __launch_bounds__(256)
-gather_sorted_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift,
-                     const uint32_t* __restrict__ vals, int stride) {
+gather_sorted_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift) {
   const BuildJob job = jobs[blockIdx.y];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= job.n_leaves * kLeaf) return;
@@ -103,7 +103,7 @@ gather_sorted_kernel(const BuildJob* __restrict__ jobs, const float* __restrict_
   if (j < job.n) {
     float sx = 0.f, sy = 0.f, sz = 0.f;
     if (shift) { sx = shift[4 * blockIdx.y]; sy = shift[4 * blockIdx.y + 1]; sz = shift[4 * blockIdx.y + 2]; }
-    uint32_t src = vals[(size_t)blockIdx.y * stride + j];
+    uint32_t src = job.order[j];
     float4 p = job.src[src];
     o = make_float4(__fsub_rn(p.x, sx), __fsub_rn(p.y, sy), __fsub_rn(p.z, sz), __int_as_float((int)src));
   } else {
@@ -154,12 +154,19 @@ __global__ void __launch_bounds__(1024) upper_levels_kernel(const BuildJob* __re
 
 }  // namespace
 
+void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std::vector<int>& n, int span,
+                      uint32_t* d_vals_out);
+
+// Orders: kd (balanced kd-tree order, kdorder.cu) for anything that is searched;
+// Morton (one radix sort) where the order only has to be spatially coherent
+// (the reading cloud: adjacent lanes should walk adjacent nodes).
 void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std::vector<int>& n,
-                   const float* d_shift, std::vector<std::unique_ptr<Index>>& out) {
+                   const float* d_shift, std::vector<std::unique_ptr<Index>>& out, IndexOrder order_kind,
+                   const std::vector<const uint32_t*>* given_order, std::vector<DBuf<uint32_t>>* keep_order) {
   const int B = (int)d_pts.size();
   out.clear();
   if (B == 0) return;
-  int max_n = 0;
+  int max_n = 0, max_P = 0, max_leaves = 0;
   std::vector<BuildJob> jobs(B);
   for (int b = 0; b < B; ++b) {
     auto idx = std::make_unique<Index>();
@@ -171,40 +178,87 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
     while ((1 << idx->depth) < idx->P) ++idx->depth;
     idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
     idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
-    jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->n, idx->n_leaves, idx->P, idx->depth};
-    if (n[b] > max_n) max_n = n[b];
+    jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->n, idx->n_leaves, idx->P, idx->depth, nullptr};
+    max_n = std::max(max_n, n[b]);
+    max_P = std::max(max_P, idx->P);
+    max_leaves = std::max(max_leaves, idx->n_leaves);
     out.push_back(std::move(idx));
   }
-  const int stride = ceil_div(max_n > 0 ? max_n : 1, kSortChunk) * kSortChunk;
+  cudaStream_t s = ctx->stream;
+  // ---- the order ------------------------------------------------------------
+  DBuf<uint32_t> ka, kb, va, vb;  // kept alive until the gather below has been enqueued (stream-ordered frees)
+  DBuf<unsigned> bbox;
+  DBuf<int> d_n;
+  if (given_order) {
+    for (int b = 0; b < B; ++b) jobs[b].order = (*given_order)[b];
+  } else if (order_kind == IndexOrder::Kd) {
+    const int span = max_P * kLeaf;
+    va.reset(ctx, (size_t)B * span);
+    kd_order_batched(ctx, d_pts, n, span, va.p);
+    for (int b = 0; b < B; ++b) jobs[b].order = va.p + (size_t)b * span;
+  } else {
+    const int stride = ceil_div(max_n > 0 ? max_n : 1, kSortChunk) * kSortChunk;
+    DBuf<BuildJob> d_jobs0(ctx, B);
+    ctx->upload_small(d_jobs0.p, jobs.data(), sizeof(BuildJob) * B);
+    d_n.reset(ctx, B);
+    ctx->upload_small(d_n.p, n.data(), sizeof(int) * B);
+    bbox.reset(ctx, (size_t)6 * B);
+    ka.reset(ctx, (size_t)B * stride); kb.reset(ctx, (size_t)B * stride);
+    va.reset(ctx, (size_t)B * stride); vb.reset(ctx, (size_t)B * stride);
+    bbox_init_kernel<<<ceil_div(6 * B, 256), 256, 0, s>>>(bbox.p, B);
+    if (max_n > 0) {
+      int nb = std::min(ceil_div(max_n, 256 * 4), 64);
+      bbox_kernel<<<dim3(nb, B), 256, 0, s>>>(d_jobs0.p, d_shift, bbox.p);
+      morton_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, s>>>(d_jobs0.p, d_shift, bbox.p, ka.p, va.p, stride);
+      ctx_count_launches(ctx, 3);
+    }
+    bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_n.p, B, stride, max_n, 30);
+    for (int b = 0; b < B; ++b) jobs[b].order = (in_b ? vb.p : va.p) + (size_t)b * stride;
+  }
+  if (keep_order) {
+    keep_order->clear();
+    for (int b = 0; b < B; ++b) {
+      keep_order->emplace_back(ctx, (size_t)std::max(n[b], 1));
+      if (n[b] > 0)
+        PGS_CUDA(cudaMemcpyAsync(keep_order->back().p, jobs[b].order, (size_t)n[b] * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  // ---- sorted points, leaf boxes, upper levels ------------------------------------
   DBuf<BuildJob> d_jobs(ctx, B);
   ctx->upload_small(d_jobs.p, jobs.data(), sizeof(BuildJob) * B);
-  DBuf<int> d_n(ctx, B);
-  ctx->upload_small(d_n.p, n.data(), sizeof(int) * B);
-  DBuf<unsigned> bbox(ctx, (size_t)6 * B);
-  DBuf<uint32_t> ka(ctx, (size_t)B * stride), kb(ctx, (size_t)B * stride), va(ctx, (size_t)B * stride),
-      vb(ctx, (size_t)B * stride);
-  cudaStream_t s = ctx->stream;
-  bbox_init_kernel<<<ceil_div(6 * B, 256), 256, 0, s>>>(bbox.p, B);
-  if (max_n > 0) {
-    int nb = std::min(ceil_div(max_n, 256 * 4), 64);
-    bbox_kernel<<<dim3(nb, B), 256, 0, s>>>(d_jobs.p, d_shift, bbox.p);
-    morton_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, s>>>(d_jobs.p, d_shift, bbox.p, ka.p, va.p, stride);
-    ctx_count_launches(ctx, 2);
-  }
-  bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_n.p, B, stride, max_n, 30);
-  const uint32_t* sorted_vals = in_b ? vb.p : va.p;
-  int max_leaves = 0, max_P = 0;
-  for (int b = 0; b < B; ++b) {
-    max_leaves = std::max(max_leaves, out[b]->n_leaves);
-    max_P = std::max(max_P, out[b]->P);
-  }
-  gather_sorted_kernel<<<dim3(ceil_div(max_leaves * kLeaf, 256), B), 256, 0, s>>>(d_jobs.p, d_shift, sorted_vals, stride);
+  gather_sorted_kernel<<<dim3(ceil_div(max_leaves * kLeaf, 256), B), 256, 0, s>>>(d_jobs.p, d_shift);
   leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
   upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-  ctx_count_launches(ctx, 4);
+  ctx_count_launches(ctx, 3);
   PGS_LAUNCH_CHECK();
-  // job tables went through the pinned ring; device temporaries are
-  // stream-ordered, so no sync is needed here.
+}
+
+// Index build for clouds, sharing the kd order between builds of the same
+// (unchanged) cloud: the SurfaceNormal filter and the matcher both need one.
+void build_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, const float* d_shift,
+                              std::vector<std::unique_ptr<Index>>& out) {
+  const int B = (int)clouds.size();
+  std::vector<const float4*> pts(B);
+  std::vector<int> n(B);
+  bool all_cached = B > 0;
+  for (int b = 0; b < B; ++b) {
+    pts[b] = clouds[b]->feat.p;
+    n[b] = (int)clouds[b]->n;
+    all_cached = all_cached && clouds[b]->kd_order && clouds[b]->kd_order_n == clouds[b]->n;
+  }
+  if (all_cached) {
+    std::vector<const uint32_t*> given(B);
+    for (int b = 0; b < B; ++b) given[b] = clouds[b]->kd_order->p;
+    build_indices(ctx, pts, n, d_shift, out, IndexOrder::Kd, &given, nullptr);
+    return;
+  }
+  std::vector<DBuf<uint32_t>> keep;
+  build_indices(ctx, pts, n, d_shift, out, IndexOrder::Kd, nullptr, &keep);
+  for (int b = 0; b < B; ++b) {
+    clouds[b]->kd_order = std::make_shared<DBuf<uint32_t>>(std::move(keep[b]));
+    clouds[b]->kd_order_n = clouds[b]->n;
+  }
 }
 
 }  // namespace pgs

@@ -297,6 +297,7 @@ void exclusive_scan_int(Ctx* ctx, const int* d_in, int* d_out, int n, int* d_tot
 
 void gather_cloud(Cloud& c, const int* d_src, int64_t m) {
   Ctx* ctx = c.ctx;
+  c.touch();
   {
     DBuf<float4> nf(ctx, (size_t)m);
     if (m > 0) {

@@ -44,8 +44,13 @@ def to_yaml(cfg) -> str:
 
 
 def rot_angle(Ra, Rb) -> float:
+    # small-angle safe (arccos of the trace is ill-conditioned near 0): the angle
+    # from the antisymmetric part, sin(theta) = |vee(R - R^T)| / 2
     R = Ra[:3, :3].T @ Rb[:3, :3]
-    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+    v = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2.0
+    s = float(np.linalg.norm(v))
+    c = (np.trace(R) - 1.0) / 2.0
+    return float(np.arctan2(s, c))
 
 
 def assert_pose_close(Ta, Tb, tol_t=1e-5, tol_r=1e-5):
