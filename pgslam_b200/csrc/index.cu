@@ -82,13 +82,15 @@ morton_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift
   float c[3] = {__fsub_rn(p.x, sx), __fsub_rn(p.y, sy), __fsub_rn(p.z, sz)};
   // one cubic grid over the longest extent keeps cells isotropic
   float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-  float scale = ext > 0.f ? 1023.0f / ext : 0.f;
+  // 8 bits per axis = 24-bit keys = 3 radix passes: the Morton order is only
+  // used where spatial COHERENCE is wanted (the reading), never for searching
+  float scale = ext > 0.f ? 255.0f / ext : 0.f;
   unsigned q[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     float f = (c[d] - lo[d]) * scale;
     int v = (int)f;
-    q[d] = (unsigned)max(0, min(1023, v));
+    q[d] = (unsigned)max(0, min(255, v));
   }
   keys[(size_t)blockIdx.y * stride + i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
   vals[(size_t)blockIdx.y * stride + i] = (uint32_t)i;
@@ -212,7 +214,7 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
       morton_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, s>>>(d_jobs0.p, d_shift, bbox.p, ka.p, va.p, stride);
       ctx_count_launches(ctx, 3);
     }
-    bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_n.p, B, stride, max_n, 30);
+    bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_n.p, B, stride, max_n, 24);
     for (int b = 0; b < B; ++b) jobs[b].order = (in_b ? vb.p : va.p) + (size_t)b * stride;
   }
   if (keep_order) {

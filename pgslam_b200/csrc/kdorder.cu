@@ -13,8 +13,8 @@
 //
 // Build, batched over clouds (blockIdx.y / job index = cloud x segment):
 //   global levels  while a segment spans more than kLocal points: per segment
-//                  bounding box -> widest axis -> key = that coordinate ->
-//                  segmented 4-pass radix sort (sort.cu, one job per segment).
+//                  bounding box -> widest axis -> key = that coordinate, 16 bits ->
+//                  segmented 2-pass radix sort (sort.cu, one job per segment).
 //                  Positional halving of a sorted segment IS the median split.
 //   local levels   one block per kLocal-point segment finishes the remaining
 //                  levels in shared memory with a bitonic network restricted
@@ -99,10 +99,19 @@ kd_key_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ v
   const int cnt = seg_count(c.n, s, S);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cnt) return;
-  const int axis = widest_axis(bbox + 6 * j);
+  const unsigned* bb = bbox + 6 * j;
+  const int axis = widest_axis(bb);
   const size_t o = (size_t)b * span + (size_t)s * S + i;
   float4 p = c.pts[vals[o]];
-  keys[o] = f2ord(axis == 0 ? p.x : (axis == 1 ? p.y : p.z));
+  // 16-bit key: the coordinate quantised over the segment's own extent.  Any
+  // order yields a valid tree (boxes come from the points); a split that is off
+  // by one 1/65536th of the extent costs nothing measurable and halves the
+  // number of radix passes per level.
+  const float lo = ord2f(bb[axis]), hi = ord2f(bb[3 + axis]);
+  const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+  const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
+  int q = (int)((x - lo) * scale);
+  keys[o] = (uint32_t)max(0, min(65535, q));
 }
 
 // ---- local levels: one block owns m0 (<= kLocal) consecutive slots ------------
@@ -231,7 +240,7 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
     kd_key_kernel<<<dim3(ceil_div(seg_max, 256), jobs), 256, 0, st>>>(clouds.p, vals_a, span, segs, S, bbox.p, keys_a.p);
     ctx_count_launches(ctx, 3);
     // jobs are laid out back to back with stride S: cloud b, segment s starts at (b*segs + s) * S
-    bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, vals_a, vals_b.p, job_n.p, jobs, S, seg_max, 32);
+    bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, vals_a, vals_b.p, job_n.p, jobs, S, seg_max, 16);
     if (in_b) throw Error(PGS_CUDA_ERROR, "kd_order: unexpected sort buffer parity");
   }
   const int m0 = std::min(span, kLocal);
