@@ -219,15 +219,20 @@ def main():
         gather(res)
         return res
 
+    def upload():
+        """H2D of one step's inputs: 2 x B clouds from pinned host memory, asynchronous on the
+        library's copy stream (public API: DataPoints(pinned_host_ptr=...))."""
+        rds = [pm.DataPoints(ctx=ctx, pinned_host_ptr=hrd.data_ptr(), n=hrd.shape[0]) for hrd, _ in host]
+        rfs = [pm.DataPoints(ctx=ctx, pinned_host_ptr=hrf.data_ptr(), n=hrf.shape[0]) for _, hrf in host]
+        return rds, rfs
+
+    pending = []
+
     def step_e2e():
-        rds, rfs = [], []
-        L = ctx.lib
-        import ctypes as C
-        for hrd, hrf in host:
-            for src, dst in ((hrd, rds), (hrf, rfs)):
-                h = C.c_void_p()
-                ctx.check(L.pgs_cloud_create(ctx.h, C.c_void_p(src.data_ptr()), src.shape[0], 0, C.byref(h)))
-                dst.append(pm.DataPoints(ctx=ctx, _handle=h))
+        # software pipeline: this step's inputs were queued on the copy stream while the
+        # previous step computed; every step still uploads its own inputs and downloads its results
+        rds, rfs = pending.pop() if pending else upload()
+        pending.append(upload())
         res = icp.compute_batch(rds, rfs)
         gather(res)
         return res

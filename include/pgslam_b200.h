@@ -14,8 +14,12 @@
  *   - T = float clouds; poses cross the ABI as double[16] (exact for floats);
  *   - no exceptions cross the ABI: every call returns a pgs_status; the text of
  *     the last failure is pgs_last_error(ctx);
- *   - `on_device != 0` means the pointer is a CUDA device pointer valid on the
- *     context's device; the call is then stream-ordered on the context stream;
+ *   - `on_device == 1` means the pointer is a CUDA device pointer valid on the
+ *     context's device; the call is then stream-ordered on the context stream.
+ *     For INPUT buffers `on_device == 2` means PINNED host memory copied
+ *     asynchronously on a side stream (overlaps with queued kernels); the caller
+ *     keeps the buffer alive and unchanged until pgs_ctx_synchronize() or the
+ *     next call that returns results to the host;
  *   - a handle is not re-entrant; distinct contexts may be driven from distinct
  *     host threads concurrently (LocalizerMT.hpp:47, LoopCloserMT.hpp:41).
  */

@@ -65,8 +65,38 @@ Params kv_params(const char* const* kv, int nkv) {
   return p;
 }
 
+void ensure_copy_stream(Ctx* ctx) {
+  if (ctx->copy_stream) return;
+  PGS_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : ctx->copy_ev) PGS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+// Upload from PINNED host memory on the side stream into a block allocated ON
+// that stream, so the copy depends on nothing queued on the compute stream and
+// overlaps with it; the compute stream joins the copy at this point of its order.
+void* upload_async(Ctx* ctx, const void* src, size_t bytes) {
+  ensure_copy_stream(ctx);
+  void* dst = nullptr;
+  PGS_CUDA(cudaMallocAsync(&dst, bytes ? bytes : 16, ctx->copy_stream));
+  if (bytes) PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  PGS_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+  PGS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+  return dst;
+}
+
 void copy_in(Ctx* ctx, void* dst, const void* src, size_t bytes, int on_device) {
   if (!bytes) return;
+  if (on_device == 2) {
+    // pinned host memory into an EXISTING compute-stream allocation: order the
+    // side stream after the allocation, the compute stream after the copy
+    ensure_copy_stream(ctx);
+    PGS_CUDA(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    PGS_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+    PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    PGS_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+    PGS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+    return;
+  }
   PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (!on_device) ctx->sync();  // the caller may reuse its host buffer right after the call
 }
@@ -147,6 +177,9 @@ void pgs_ctx_destroy(pgs_ctx* ctx) {
   if (ctx->c.h_progress) cudaFreeHost((void*)ctx->c.h_progress);
   for (auto& e : ctx->c.loop_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->c.copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }
@@ -222,8 +255,12 @@ pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, i
   auto h = std::make_unique<pgs_cloud>();
   h->c = std::make_unique<Cloud>(&ctx->c);
   h->c->n = n;
-  h->c->feat.reset(&ctx->c, (size_t)n);
-  copy_in(&ctx->c, h->c->feat.p, features4xN, (size_t)n * sizeof(float4), on_device);
+  if (on_device == 2) {
+    h->c->feat.adopt(&ctx->c, static_cast<float4*>(upload_async(&ctx->c, features4xN, (size_t)n * sizeof(float4))), (size_t)n);
+  } else {
+    h->c->feat.reset(&ctx->c, (size_t)n);
+    copy_in(&ctx->c, h->c->feat.p, features4xN, (size_t)n * sizeof(float4), on_device);
+  }
   *out = h.release();
   PGS_API_END(&ctx->c)
 }

@@ -78,8 +78,9 @@ void Cloud::remove(const std::string& label) {
 std::unique_ptr<Cloud> Cloud::clone() const {
   auto c = std::make_unique<Cloud>(ctx);
   c->n = n;
-  c->kd_order = kd_order;  // same points, same order
+  c->kd_order = kd_order;  // same points, same order, same index
   c->kd_order_n = kd_order_n;
+  c->index_cache = index_cache;
   c->feat.reset(ctx, (size_t)n);
   if (n) PGS_CUDA(cudaMemcpyAsync(c->feat.p, feat.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   for (auto& d : descs) {

@@ -60,6 +60,8 @@ struct Ctx {
   volatile int* h_progress = nullptr;  // mapped host word: set to 1 by the device when no pair is active
   volatile int* d_progress = nullptr;  // device alias of h_progress
   cudaEvent_t loop_ev[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;  // uploads from pinned host memory overlap with compute
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   void ensure_progress();
 
   void* alloc(size_t bytes);
@@ -91,6 +93,13 @@ struct DBuf {
     ctx = c;
     n = count;
     p = static_cast<T*>(c->alloc((count ? count : 1) * sizeof(T)));
+  }
+  // take ownership of a block allocated elsewhere in the same pool (freed on ctx's stream)
+  void adopt(Ctx* c, T* ptr, size_t count) {
+    release();
+    ctx = c;
+    p = ptr;
+    n = count;
   }
   void release() {
     if (p && ctx) ctx->free(p);

@@ -24,6 +24,8 @@ struct Desc {
   DBuf<float> data;
 };
 
+struct Index;
+
 struct Cloud {
   Ctx* ctx = nullptr;
   int64_t n = 0;
@@ -33,7 +35,8 @@ struct Cloud {
   // function that moves, adds or removes points calls touch()
   std::shared_ptr<DBuf<uint32_t>> kd_order;
   int64_t kd_order_n = -1;
-  void touch() { kd_order.reset(); kd_order_n = -1; }
+  std::shared_ptr<Index> index_cache;  // index of the un-shifted points, same validity
+  void touch() { kd_order.reset(); kd_order_n = -1; index_cache.reset(); }
 
   explicit Cloud(Ctx* c) : ctx(c) {}
   Desc* find(const std::string& label) {
@@ -107,6 +110,11 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
 // same for clouds; caches / reuses the kd order in the Cloud objects
 void build_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, const float* d_shift,
                               std::vector<std::unique_ptr<Index>>& out);
+// un-shifted index of each cloud, built once and cached in the cloud
+void cached_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, std::vector<std::shared_ptr<Index>>& out);
+// mean-centred copies of existing indices (one streaming kernel)
+void derive_shifted_indices(Ctx* ctx, const std::vector<const Index*>& src, const float* d_shift,
+                            std::vector<std::unique_ptr<Index>>& out);
 
 // ---------------------------------------------------------------------------
 // exact kNN (eps = 0, ties -> lower original index), k <= 32.

@@ -363,8 +363,8 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   const int B = (int)clouds.size();
   std::vector<int> ns(B);
   for (int b = 0; b < B; ++b) ns[b] = (int)clouds[b]->n;
-  std::vector<std::unique_ptr<Index>> idx;
-  build_indices_for_clouds(ctx, clouds, nullptr, idx);
+  std::vector<std::shared_ptr<Index>> idx;
+  cached_indices_for_clouds(ctx, clouds, idx);
   std::vector<DBuf<int32_t>> ids(B);
   std::vector<DBuf<float>> d2(B);
   std::vector<const Index*> ip(B);

@@ -983,9 +983,25 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
   std::vector<int> ns(B);
   for (int b = 0; b < B; ++b) ns[b] = (int)rp[b]->n;
   std::vector<std::unique_ptr<Index>> idx;
-  // the kd order is translation invariant: if the SurfaceNormal filter already
-  // built it for this (unchanged) cloud it is reused here
-  build_indices_for_clouds(ctx, rp, centre_first ? nullptr : shift.p, idx);
+  {
+    // the un-shifted index is shared with the SurfaceNormal filter (cached in
+    // the cloud); the matcher's mean-centred index is a shifted copy of it
+    std::vector<std::shared_ptr<Index>> base;
+    cached_indices_for_clouds(ctx, rp, base);
+    if (centre_first) {
+      // setMap centred the points themselves before the filters: nothing to shift
+      idx.resize(B);
+      std::vector<const Index*> src(B);
+      for (int b = 0; b < B; ++b) src[b] = base[b].get();
+      DBuf<float> zero(ctx, (size_t)4 * B);
+      zero.zero();
+      derive_shifted_indices(ctx, src, zero.p, idx);
+    } else {
+      std::vector<const Index*> src(B);
+      for (int b = 0; b < B; ++b) src[b] = base[b].get();
+      derive_shifted_indices(ctx, src, shift.p, idx);
+    }
+  }
   std::vector<double> hT((size_t)16 * B);
   Tmean.download(hT.data(), hT.size());
   out.clear();

@@ -165,6 +165,7 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
 void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std::vector<int>& n,
                    const float* d_shift, std::vector<std::unique_ptr<Index>>& out, IndexOrder order_kind,
                    const std::vector<const uint32_t*>* given_order, std::vector<DBuf<uint32_t>>* keep_order) {
+  const bool want_boxes = order_kind == IndexOrder::Kd;  // a Morton-ordered cloud is never searched
   const int B = (int)d_pts.size();
   out.clear();
   if (B == 0) return;
@@ -230,9 +231,69 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
   DBuf<BuildJob> d_jobs(ctx, B);
   ctx->upload_small(d_jobs.p, jobs.data(), sizeof(BuildJob) * B);
   gather_sorted_kernel<<<dim3(ceil_div(max_leaves * kLeaf, 256), B), 256, 0, s>>>(d_jobs.p, d_shift);
-  leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
-  upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-  ctx_count_launches(ctx, 3);
+  ctx_count_launches(ctx, 1);
+  if (want_boxes) {
+    leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
+    upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
+    ctx_count_launches(ctx, 2);
+  }
+  PGS_LAUNCH_CHECK();
+}
+
+namespace {
+struct ShiftJob {
+  const float4* src_pts;
+  const float* src_nodes;
+  float4* dst_pts;
+  float* dst_nodes;
+  int n_pts;    // n_leaves * kLeaf
+  int n_nodes;  // 2 * P
+};
+
+// fl(x - m) is monotone in x, so the box of the shifted points is exactly the
+// shifted box and the kd order is unchanged: a mean-centred copy of an index is
+// one streaming pass, not a rebuild.
+__global__ void __launch_bounds__(256)
+shift_index_kernel(const ShiftJob* __restrict__ jobs, const float* __restrict__ shift) {
+  const ShiftJob job = jobs[blockIdx.y];
+  const float sx = shift[4 * blockIdx.y], sy = shift[4 * blockIdx.y + 1], sz = shift[4 * blockIdx.y + 2];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < job.n_pts) {
+    float4 p = job.src_pts[i];
+    // padding (+inf) stays +inf
+    job.dst_pts[i] = make_float4(__fsub_rn(p.x, sx), __fsub_rn(p.y, sy), __fsub_rn(p.z, sz), p.w);
+  }
+  if (i < job.n_nodes) {
+    const float* a = job.src_nodes + (size_t)i * 6;
+    float* o = job.dst_nodes + (size_t)i * 6;
+    // empty boxes (+inf / -inf) stay empty
+    o[0] = __fsub_rn(a[0], sx); o[1] = __fsub_rn(a[1], sy); o[2] = __fsub_rn(a[2], sz);
+    o[3] = __fsub_rn(a[3], sx); o[4] = __fsub_rn(a[4], sy); o[5] = __fsub_rn(a[5], sz);
+  }
+}
+}  // namespace
+
+void derive_shifted_indices(Ctx* ctx, const std::vector<const Index*>& src, const float* d_shift,
+                            std::vector<std::unique_ptr<Index>>& out) {
+  const int B = (int)src.size();
+  out.clear();
+  std::vector<ShiftJob> jobs(B);
+  int max_items = 1;
+  for (int b = 0; b < B; ++b) {
+    auto idx = std::make_unique<Index>();
+    idx->ctx = ctx;
+    idx->n = src[b]->n; idx->n_leaves = src[b]->n_leaves; idx->P = src[b]->P; idx->depth = src[b]->depth;
+    idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
+    idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
+    jobs[b] = ShiftJob{src[b]->pts.p, src[b]->nodes.p, idx->pts.p, idx->nodes.p, idx->n_leaves * kLeaf, 2 * idx->P};
+    max_items = std::max(max_items, std::max(jobs[b].n_pts, jobs[b].n_nodes));
+    out.push_back(std::move(idx));
+  }
+  if (B == 0) return;
+  DBuf<ShiftJob> d_jobs(ctx, B);
+  ctx->upload_small(d_jobs.p, jobs.data(), sizeof(ShiftJob) * B);
+  shift_index_kernel<<<dim3(ceil_div(max_items, 256), B), 256, 0, ctx->stream>>>(d_jobs.p, d_shift);
+  ctx_count_launches(ctx, 1);
   PGS_LAUNCH_CHECK();
 }
 
@@ -261,6 +322,22 @@ void build_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, const
     clouds[b]->kd_order = std::make_shared<DBuf<uint32_t>>(std::move(keep[b]));
     clouds[b]->kd_order_n = clouds[b]->n;
   }
+}
+
+// Unshifted index of every cloud, cached in the cloud (shared with its clones)
+// until its points change.
+void cached_indices_for_clouds(Ctx* ctx, const std::vector<Cloud*>& clouds, std::vector<std::shared_ptr<Index>>& out) {
+  const int B = (int)clouds.size();
+  out.assign(B, nullptr);
+  std::vector<Cloud*> todo;
+  for (int b = 0; b < B; ++b)
+    if (!(clouds[b]->index_cache && clouds[b]->index_cache->n == clouds[b]->n && clouds[b]->kd_order)) todo.push_back(clouds[b]);
+  if (!todo.empty()) {
+    std::vector<std::unique_ptr<Index>> built;
+    build_indices_for_clouds(ctx, todo, nullptr, built);
+    for (size_t t = 0; t < todo.size(); ++t) todo[t]->index_cache = std::shared_ptr<Index>(std::move(built[t]));
+  }
+  for (int b = 0; b < B; ++b) out[b] = clouds[b]->index_cache;
 }
 
 }  // namespace pgs

@@ -248,14 +248,20 @@ class DataPoints:
     descriptors: {label: span x N float32}."""
 
     def __init__(self, features=None, descriptors: dict | None = None, ctx: Context | None = None,
-                 _handle=None, device_ptr: int | None = None, n: int | None = None):
+                 _handle=None, device_ptr: int | None = None, n: int | None = None,
+                 pinned_host_ptr: int | None = None):
         self.ctx = ctx or default_context()
         L = self.ctx.lib
         if _handle is not None:
             self.h = _handle
             return
         h = _vp()
-        if device_ptr is not None:
+        if pinned_host_ptr is not None:
+            # N x 4 float32 in PINNED host memory, uploaded asynchronously on the side
+            # stream (mode 2 of the ABI): the caller keeps the buffer alive until the
+            # next call that returns results
+            self.ctx.check(L.pgs_cloud_create(self.ctx.h, _vp(pinned_host_ptr), n, 2, C.byref(h)))
+        elif device_ptr is not None:
             self.ctx.check(L.pgs_cloud_create(self.ctx.h, _vp(device_ptr), n, 1, C.byref(h)))
         else:
             f = np.asarray(features, dtype=np.float32)
