@@ -145,7 +145,17 @@ def cpu_reference_run(steps, warmup, sample_pairs=1):
                        f"OpenMP over queries on {threads} host thread(s)")
 
 
+def emit(line: dict, fd: int):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # exactly ONE line may reach stdout: native libraries (NCCL prints its version)
+    # write to fd 1 behind Python's back, so fd 1 is pointed at stderr for the
+    # whole run and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -174,7 +184,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "iterations": r["iterations"]}
-        print(json.dumps(line))
+        emit(line, out_fd)
         return
 
     # --------------------------------------------------------------------- ours
@@ -326,7 +336,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "iterations_mean": statistics.mean(iters), "pairs_ok": ok,
             "single_pair_latency_ms": ms_one / 10.0}
-    print(json.dumps(line))
+    emit(line, out_fd)
     if multi:
         dist.destroy_process_group()
 

@@ -37,7 +37,7 @@ __host__ __device__ inline int reduce_slices(int n, int per_block, int max_block
   int s = (n + per_block - 1) / per_block;
   return s < 1 ? 1 : (s > max_blocks ? max_blocks : s);
 }
-constexpr int kAccPerBlock = 2048;
+constexpr int kAccPerBlock = 4096;
 constexpr int kAccMaxBlocks = 128;
 
 // ---------------------------------------------------------------------------
