@@ -517,3 +517,99 @@ def test_full_size_properties_120k(pm, pair120k):
         {"DifferentialTransformationChecker": {"minDiffRotErr": 1e-6, "minDiffTransErr": 1e-6}}])))
     out = icp(pm.DataPoints(moved), ref)
     np.testing.assert_allclose(out, T, atol=2e-5)
+
+
+# ------------------------------------------------------ BASELINE configs C3 / C5, threading ---
+def test_c5_one_million_point_scan_to_map(pm):
+    """configs[4]: ~1M-point reading vs 1M-point map, voxel subsampling, trimmed 0.75."""
+    scene = synth.make_scene(77)
+    T_ref = synth.pose_matrix([0.0, 0.0, synth.SENSOR_HEIGHT])
+    T_rd = synth.pose_matrix([0.25, -0.15, synth.SENSOR_HEIGHT + 0.03], np.deg2rad(1.5), 0.004, -0.006)
+    rf = synth.velodyne_scan(77, 0, T_ref, beams=128, az_steps=7812, scene=scene)
+    rd = synth.velodyne_scan(77, 1, T_rd, beams=128, az_steps=7812, scene=scene)
+    assert rd.shape[1] == 999936
+    icp, T, want = _run_both(pm, util.C5, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    assert icp.last["n_reference"] == rf.shape[1] and icp.last["n_reading"] < 0.5 * rd.shape[1]
+    util.assert_pose_close(T, want["T"])
+    truth = np.linalg.inv(T_ref) @ T_rd
+    assert np.abs(T[:3, 3] - truth[:3, 3]).max() < 0.05  # the default checkers stop within a few cm
+
+
+def test_c3_sequential_scan_to_map_odometry(pm):
+    """configs[2] in miniature: ICPSequence against a 3-keyframe local map assembled on the
+    device the way LocalMap::BuildCloudFromData does, each scan seeded by the previous pose
+    (Localizer.hpp:119-126); the oracle walks the same chain."""
+    scene = synth.make_scene(5)
+    poses = synth.trajectory(8, step=0.5, turn_deg=2.0)
+    scans = [synth.velodyne_scan(5, i, poses[i], beams=32, az_steps=900, scene=scene) for i in range(8)]
+    kf = [0, 1, 2]
+    T_ref_kf = [np.linalg.inv(poses[kf[-1]]) @ poses[k] for k in kf]  # keyframes in the reference-kf frame
+    filt = pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS[:3]))
+    dps = []
+    ocs = []
+    for k in kf:
+        dp = pm.DataPoints(scans[k])
+        filt.apply(dp)
+        dps.append(dp)
+        oc = ob.Cloud(scans[k])
+        for it in util.INPUT_FILTERS[:3]:
+            (name, p), = ob._modlist([it])
+            ob.apply_filter(oc, name, **p)
+        ocs.append(oc)
+    # reference keyframe first, the others transformed into its frame and concatenated
+    local_map = pm.assemble_local_map([dps[2], dps[1], dps[0]], [np.eye(4), T_ref_kf[1], T_ref_kf[0]])
+    omap = ocs[2].copy()
+    for oc, T in ((ocs[1], T_ref_kf[1]), (ocs[0], T_ref_kf[0])):
+        t = oc.copy()
+        assert ob.rigid_transform(t, T) == 0
+        ob.lib().orc_cloud_concatenate(omap.ptr, t.ptr)
+    assert local_map.getNbPoints() == omap.n == 3 * scans[0].shape[1]
+    assert np.array_equal(local_map.features.view(np.uint32), omap.features.view(np.uint32))
+    assert np.array_equal(local_map.getDescriptorByName("normals").view(np.uint32), omap.desc("normals").view(np.uint32))
+    cfg = dict(util.C2, referenceDataPointsFilters=[])  # the local map already carries normals
+    seq = pm.ICPSequence()
+    seq.loadFromYaml(util.to_yaml(cfg))
+    seq.setMap(local_map)
+    oseq = ob.IcpSequence(cfg)
+    assert oseq.set_map(omap) == 0
+    T_prev = np.eye(4)
+    for i in range(3, 8):
+        guess = T_prev @ (np.linalg.inv(poses[i - 1]) @ poses[i]) if i > 3 else np.linalg.inv(poses[2]) @ poses[3]
+        T = seq(pm.DataPoints(scans[i]), guess)
+        want = oseq.run(ob.Cloud(scans[i]), guess)
+        assert want["status"] == 0 and seq.last["iterations"] == want["iterations"]
+        util.assert_pose_close(T, want["T"])
+        truth = np.linalg.inv(poses[2]) @ poses[i]
+        assert np.abs(T[:3, 3] - truth[:3, 3]).max() < 0.1  # sanity only; parity is against the oracle
+        T_prev = want["T"]
+
+
+def test_two_host_threads_two_contexts(pm):
+    """pgslam-MT: localizer and loop closer register concurrently from two host threads,
+    each on its own objects (LocalizerMT.hpp:47, LoopCloserMT.hpp:41)."""
+    import threading
+    pairs = [synth.scan_pair(30 + s, beams=16, az_steps=700) for s in range(2)]
+    serial = []
+    for rd, rf, _ in pairs:
+        icp = pm.ICP()
+        icp.loadFromYaml(util.to_yaml(util.C2))
+        serial.append((icp(pm.DataPoints(rd), pm.DataPoints(rf)), icp.last["iterations"]))
+    out = [None, None]
+
+    def worker(i):
+        c = pm.Context(0)
+        icp = pm.ICP(c)
+        icp.loadFromYaml(util.to_yaml(util.C2))
+        rd, rf, _ = pairs[i]
+        for _ in range(5):
+            T = icp(pm.DataPoints(rd, ctx=c), pm.DataPoints(rf, ctx=c))
+        out[i] = (T, icp.last["iterations"])
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(2):
+        assert out[i] is not None and out[i][1] == serial[i][1]
+        assert np.array_equal(out[i][0], serial[i][0])
