@@ -309,8 +309,19 @@ def main():
     match_s = stage["match_ms"] / 1e3
     peak, peak_src = peaks()
     achieved = alg_bytes / match_s / 1e9 if match_s > 0 else 0.0
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture,
+    # valid only for the batch size it was captured at
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_match_kernel_ncu_full.json")) as f:
+            cap = json.load(f)
+        if cap.get("pairs") == B:
+            traffic = cap["dram_traffic_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "match_kernel (fused rigid transform + exact k=1 NN traversal)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch_all_pairs_active": sum(24.0 * r["n_reading"] + 16.0 * r["n_reference"] for r in res),
                 "peak_source": peak_src, "launches": stage["iterations_launched"],
                 "avg_launch_ms": stage["match_ms"] / max(stage["iterations_launched"], 1),
                 "algorithmic_bytes_per_step": alg_bytes,

@@ -1,10 +1,10 @@
 // index.cu — the spatial index that replaces libnabo's kd-tree
 // (KDTreeMatcher::init -> NNS::create).
 //
-// B200 shape instead of a pointer-built unbalanced kd-tree: points are sorted
-// by 30-bit Morton code on the device, cut into leaves of kLeaf consecutive
-// points (one 128-byte line of float4 each), and covered by an implicit
-// complete binary tree of axis-aligned boxes.  No child pointers: node i has
+// B200 shape instead of a pointer-built unbalanced kd-tree: points are put in
+// balanced kd-tree order on the device (kdorder.cu), cut into leaves of kLeaf
+// consecutive points (one 128-byte line of float4 each), and covered by an
+// implicit complete binary tree of axis-aligned boxes.  No child pointers: node i has
 // children 2i and 2i+1, stored adjacently (48 bytes = three float4 loads), and
 // traversal needs no stack (see knn.cu).  Exactness of the search does not
 // depend on the tree shape, only on the boxes being conservative, so parity
