@@ -281,7 +281,7 @@ def main():
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    for _ in range(1):
+    for _ in range(args.warmup):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 

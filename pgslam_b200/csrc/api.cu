@@ -74,13 +74,13 @@ void ensure_copy_stream(Ctx* ctx) {
 // Upload from PINNED host memory on the side stream into a block allocated ON
 // that stream, so the copy depends on nothing queued on the compute stream and
 // overlaps with it; the compute stream joins the copy at this point of its order.
-void* upload_async(Ctx* ctx, const void* src, size_t bytes) {
+void* upload_async(Ctx* ctx, const void* src, size_t bytes, cudaEvent_t* ready) {
   ensure_copy_stream(ctx);
   void* dst = nullptr;
   PGS_CUDA(cudaMallocAsync(&dst, bytes ? bytes : 16, ctx->copy_stream));
   if (bytes) PGS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-  PGS_CUDA(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
-  PGS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+  PGS_CUDA(cudaEventCreateWithFlags(ready, cudaEventDisableTiming));
+  PGS_CUDA(cudaEventRecord(*ready, ctx->copy_stream));
   return dst;
 }
 
@@ -256,7 +256,8 @@ pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, i
   h->c = std::make_unique<Cloud>(&ctx->c);
   h->c->n = n;
   if (on_device == 2) {
-    h->c->feat.adopt(&ctx->c, static_cast<float4*>(upload_async(&ctx->c, features4xN, (size_t)n * sizeof(float4))), (size_t)n);
+    h->c->feat.adopt(&ctx->c, static_cast<float4*>(upload_async(&ctx->c, features4xN, (size_t)n * sizeof(float4), &h->c->ready)),
+                     (size_t)n);
   } else {
     h->c->feat.reset(&ctx->c, (size_t)n);
     copy_in(&ctx->c, h->c->feat.p, features4xN, (size_t)n * sizeof(float4), on_device);
@@ -268,6 +269,7 @@ pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, i
 pgs_status pgs_cloud_set_descriptor(pgs_cloud* c, const char* label, int span, const float* data, int on_device) {
   Ctx* ctx = c->c->ctx;
   PGS_API_BEGIN
+  c->c->wait_ready();
   if (span <= 0 || !label) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_set_descriptor: bad arguments");
   Desc& d = c->c->add(label, span);
   copy_in(ctx, d.data.p, data, (size_t)c->c->n * span * sizeof(float), on_device);
@@ -301,6 +303,7 @@ pgs_status pgs_cloud_descriptor_info(const pgs_cloud* c, int index, char* label,
 pgs_status pgs_cloud_get_features(const pgs_cloud* c, float* out4xN, int on_device) {
   Ctx* ctx = c->c->ctx;
   PGS_API_BEGIN
+  c->c->wait_ready();
   copy_out(ctx, out4xN, c->c->feat.p, (size_t)c->c->n * sizeof(float4), on_device);
   PGS_API_END(ctx)
 }
@@ -308,6 +311,7 @@ pgs_status pgs_cloud_get_features(const pgs_cloud* c, float* out4xN, int on_devi
 pgs_status pgs_cloud_get_descriptor(const pgs_cloud* c, const char* label, float* out, int on_device) {
   Ctx* ctx = c->c->ctx;
   PGS_API_BEGIN
+  c->c->wait_ready();
   const Desc* d = c->c->find(label);
   if (!d) throw Error(PGS_INVALID_FIELD, std::string("Cannot find descriptor ") + label);
   copy_out(ctx, out, d->data.p, (size_t)c->c->n * d->span * sizeof(float), on_device);
@@ -317,6 +321,7 @@ pgs_status pgs_cloud_get_descriptor(const pgs_cloud* c, const char* label, float
 pgs_status pgs_cloud_copy(const pgs_cloud* c, pgs_cloud** out) {
   Ctx* ctx = c->c->ctx;
   PGS_API_BEGIN
+  c->c->wait_ready();
   auto h = std::make_unique<pgs_cloud>();
   h->c = c->c->clone();
   *out = h.release();
@@ -326,6 +331,7 @@ pgs_status pgs_cloud_copy(const pgs_cloud* c, pgs_cloud** out) {
 pgs_status pgs_cloud_concatenate(pgs_cloud* a, const pgs_cloud* b) {
   Ctx* ctx = a->c->ctx;
   PGS_API_BEGIN
+  a->c->wait_ready(); b->c->wait_ready();
   concatenate_cloud(*a->c, *b->c);
   PGS_API_END(ctx)
 }
@@ -336,6 +342,7 @@ void pgs_cloud_destroy(pgs_cloud* c) { delete c; }
 pgs_status pgs_rigid_transform(pgs_cloud* c, const double T[16]) {
   Ctx* ctx = c->c->ctx;
   PGS_API_BEGIN
+  c->c->wait_ready();
   rigid_transform_cloud(*c->c, T);
   PGS_API_END(ctx)
 }
@@ -343,6 +350,7 @@ pgs_status pgs_rigid_transform(pgs_cloud* c, const double T[16]) {
 pgs_status pgs_cloud_assemble(pgs_ctx* ctx, int n, const pgs_cloud* const* clouds, const double* T, pgs_cloud** out) {
   PGS_API_BEGIN
   if (n < 1) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_assemble: need at least one cloud");
+  for (int i = 0; i < n; ++i) clouds[i]->c->wait_ready();
   auto h = std::make_unique<pgs_cloud>();
   h->c = clouds[0]->c->clone();
   for (int i = 1; i < n; ++i) {
@@ -383,6 +391,7 @@ int pgs_filters_count(const pgs_filters* f) { return (int)f->mods.size(); }
 
 pgs_status pgs_filters_apply(pgs_filters* f, pgs_cloud* c) {
   PGS_API_BEGIN
+  c->c->wait_ready();
   std::vector<Cloud*> cl{c->c.get()};
   apply_filters(f->ctx, f->mods, cl);
   PGS_API_END(f->ctx)
@@ -403,6 +412,7 @@ pgs_status pgs_matcher_create(pgs_ctx* ctx, const char* name, const char* const*
 
 pgs_status pgs_matcher_init(pgs_matcher* m, const pgs_cloud* reference) {
   PGS_API_BEGIN
+  reference->c->wait_ready();
   std::vector<std::unique_ptr<Index>> idx;
   build_indices(m->ctx, {reference->c->feat.p}, {(int)reference->c->n}, nullptr, idx);
   m->index = std::move(idx[0]);
@@ -413,6 +423,7 @@ int pgs_matcher_knn(const pgs_matcher* m) { return (int)m->mod.integer("knn"); }
 
 pgs_status pgs_matcher_find(pgs_matcher* m, const pgs_cloud* reading, int32_t* ids, float* dists2, int on_device) {
   PGS_API_BEGIN
+  reading->c->wait_ready();
   const int k = (int)m->mod.integer("knn");
   const size_t cnt = (size_t)reading->c->n * k;
   if (on_device) {
@@ -478,6 +489,7 @@ pgs_status pgs_minimizer_compute(pgs_minimizer* e, const pgs_cloud* reading, con
                                  const int32_t* ids, const float* dists2, const float* weights, int k, int on_device,
                                  pgs_min_result* out) {
   PGS_API_BEGIN
+  reading->c->wait_ready(); reference->c->wait_ready();
   const size_t nk = (size_t)reading->c->n * k;
   if (on_device) {
     minimize_device(e->ctx, e->mod, *reading->c, *reference->c, ids, dists2, weights, k, out);
@@ -527,6 +539,7 @@ pgs_minimizer* pgs_icp_minimizer(pgs_icp* icp) { return &icp->minimizer; }
 pgs_status pgs_icp_run(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference, const double T_init[16],
                        pgs_icp_result* out) {
   PGS_API_BEGIN
+  reading->c->wait_ready(); reference->c->wait_ready();
   std::vector<const Cloud*> rd{reading->c.get()}, rf{reference->c.get()};
   engine_of(icp).run_batch(rd, rf, T_init, out);
   if (out->status != PGS_OK) {
@@ -540,6 +553,7 @@ pgs_status pgs_icp_run(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* 
 
 pgs_status pgs_icp_set_map(pgs_icp* icp, const pgs_cloud* map) {
   PGS_API_BEGIN
+  map->c->wait_ready();
   engine_of(icp).set_map(*map->c);
   PGS_API_END(icp->ctx)
 }
@@ -548,6 +562,7 @@ int pgs_icp_has_map(const pgs_icp* icp) { return icp->engine && icp->engine->has
 
 pgs_status pgs_icp_run_sequence(pgs_icp* icp, const pgs_cloud* reading, const double T_init[16], pgs_icp_result* out) {
   PGS_API_BEGIN
+  reading->c->wait_ready();
   engine_of(icp).run_sequence(*reading->c, T_init, out);
   if (out->status != PGS_OK) return fail(icp->ctx, out->status, "ICPSequence failed for this reading");
   PGS_API_END(icp->ctx)
@@ -558,7 +573,12 @@ pgs_status pgs_icp_run_batch(pgs_icp* icp, int n_pairs, const pgs_cloud* const* 
   PGS_API_BEGIN
   if (n_pairs <= 0) return PGS_OK;
   std::vector<const Cloud*> rd(n_pairs), rf(n_pairs);
-  for (int i = 0; i < n_pairs; ++i) { rd[i] = readings[i]->c.get(); rf[i] = references[i]->c.get(); }
+  for (int i = 0; i < n_pairs; ++i) {
+    readings[i]->c->wait_ready();
+    references[i]->c->wait_ready();
+    rd[i] = readings[i]->c.get();
+    rf[i] = references[i]->c.get();
+  }
   engine_of(icp).run_batch(rd, rf, T_inits, results);
   bool any_ok = false;
   int first_bad = PGS_OK;
@@ -573,6 +593,7 @@ pgs_status pgs_icp_run_batch(pgs_icp* icp, int n_pairs, const pgs_cloud* const* 
 pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
                                  const double T_world_robot[16], double* weighted_point_used_ratio) {
   PGS_API_BEGIN
+  reading->c->wait_ready(); reference->c->wait_ready();
   Ctx* ctx = icp->ctx;
   // Localizer.hpp:309-347, module by module, without leaving the device
   auto ref = reference->c->clone();
@@ -605,6 +626,7 @@ pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const p
 pgs_status pgs_icp_probe_residual(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
                                   const double T[16], double* residual) {
   PGS_API_BEGIN
+  reading->c->wait_ready(); reference->c->wait_ready();
   Ctx* ctx = icp->ctx;
   // LoopCloser.hpp:346-362: raw candidate cloud, un-centred, unfiltered
   auto rd = reading->c->clone();

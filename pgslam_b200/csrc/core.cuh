@@ -37,6 +37,17 @@ struct Cloud {
   int64_t kd_order_n = -1;
   std::shared_ptr<Index> index_cache;  // index of the un-shifted points, same validity
   void touch() { kd_order.reset(); kd_order_n = -1; index_cache.reset(); }
+  // set when the features are still being uploaded on the context's copy stream:
+  // the compute stream joins that copy at the FIRST USE of the cloud, not at its
+  // creation, so an upload queued for the next batch overlaps this batch's kernels
+  mutable cudaEvent_t ready = nullptr;
+  void wait_ready() const {
+    if (!ready) return;
+    cudaStreamWaitEvent(ctx->stream, ready, 0);
+    cudaEventDestroy(ready);
+    ready = nullptr;
+  }
+  ~Cloud() { wait_ready(); }
 
   explicit Cloud(Ctx* c) : ctx(c) {}
   Desc* find(const std::string& label) {
