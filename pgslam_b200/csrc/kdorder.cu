@@ -115,48 +115,71 @@ kd_key_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ v
 }
 
 // ---- local levels: one block owns m0 (<= kLocal) consecutive slots ------------
+//
+// Sub-segments of kRadixMin points or more are SPLIT, not sorted: only the median
+// partition matters (both halves are re-split along their own axis one level
+// down).  Per level: bounding box -> widest axis -> 16-bit key -> two 256-bin
+// histogram passes find the exact median key and how many of its ties go left
+// -> one stable partition pass (per-32-chunk counts + prefix, deterministic).
+// Smaller sub-segments are sorted with a bitonic network whose strides stay
+// inside a warp's window, so they need almost no block barriers.
+constexpr int kRadixMin = 256;
+constexpr int kMaxRadixSegs = kLocal / kRadixMin;  // 16
+constexpr int kChunks = kLocal / 32;               // 128
+
 __global__ void __launch_bounds__(kLocalThreads)
 kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals, int span, int segs, int m0) {
   extern __shared__ unsigned smem[];
   unsigned* sx = smem;                 // ordered-uint coordinates, fixed slots
   unsigned* sy = sx + kLocal;
   unsigned* sz = sy + kLocal;
-  unsigned* sid = sz + kLocal;         // original index per slot
-  unsigned* key = sid + kLocal;        // sort key per position
+  unsigned* key = sz + kLocal;         // key per position (16-bit in radix levels, 32-bit in bitonic levels)
   unsigned* bb = key + kLocal;         // 6 x (kLocal / 16) bounding boxes
-  unsigned short* perm = reinterpret_cast<unsigned short*>(bb + 6 * (kLocal / 16));  // slot per position
-  unsigned char* axis = reinterpret_cast<unsigned char*>(perm + kLocal);
+  unsigned* hist = bb + 6 * (kLocal / 16);            // kMaxRadixSegs x 256
+  int* seg_less = reinterpret_cast<int*>(hist + kMaxRadixSegs * 256);  // per radix segment
+  int* seg_eq = seg_less + kMaxRadixSegs;
+  int* seg_tie = seg_eq + kMaxRadixSegs;
+  int* seg_b1 = seg_tie + kMaxRadixSegs;
+  int* seg_below = seg_b1 + kMaxRadixSegs;
+  int* seg_kp = seg_below + kMaxRadixSegs;
+  unsigned short* perm_a = reinterpret_cast<unsigned short*>(seg_kp + kMaxRadixSegs);  // slot per position
+  unsigned short* perm_b = perm_a + kLocal;
+  unsigned short* ch_l = perm_b + kLocal;  // per 32-chunk counts, then exclusive offsets
+  unsigned short* ch_e = ch_l + kChunks;
+  unsigned short* ch_ol = ch_e + kChunks;
+  unsigned short* ch_oe = ch_ol + kChunks;
+  unsigned char* axis = reinterpret_cast<unsigned char*>(ch_oe + kChunks);
 
   const int b = blockIdx.y, s = blockIdx.x;
   const KdCloud c = clouds[b];
   const int cnt = seg_count(c.n, s, m0);
   if (cnt == 0) return;
   uint32_t* v = vals + (size_t)b * span + (size_t)s * m0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned short* perm = perm_a;
+  unsigned short* perm_next = perm_b;
   for (int i = tid; i < m0; i += kLocalThreads) {
+    // slot i is a real point iff i < cnt (the original indices stay in global memory)
     if (i < cnt) {
-      const uint32_t id = v[i];
-      float4 p = c.pts[id];
+      float4 p = c.pts[v[i]];
       sx[i] = f2ord(p.x); sy[i] = f2ord(p.y); sz[i] = f2ord(p.z);
-      sid[i] = id;
     } else {
       sx[i] = sy[i] = sz[i] = 0xffffffffu;  // padding sorts last on every axis
-      sid[i] = 0xffffffffu;
     }
     perm[i] = (unsigned short)i;
   }
   __syncthreads();
   for (int m = m0; m > kLeaf; m >>= 1) {
     const int nseg = m0 / m;
+    // ---- bounding box of every sub-segment (real points only) -> widest axis ----
     for (int q = tid; q < nseg * 6; q += kLocalThreads) bb[q] = (q % 6 < 3) ? 0xffffffffu : 0u;
     __syncthreads();
-    // bounding box of every sub-segment (real points only): lanes of a warp (or
-    // of a half-warp when m == 16) share a sub-segment, so reduce before the atomics
     for (int i = tid; i < m0; i += kLocalThreads) {
       const int slot = perm[i];
-      const bool real = sid[slot] != 0xffffffffu;
+      const bool real = slot < cnt;
       unsigned lo[3] = {real ? sx[slot] : 0xffffffffu, real ? sy[slot] : 0xffffffffu, real ? sz[slot] : 0xffffffffu};
       unsigned hi[3] = {real ? sx[slot] : 0u, real ? sy[slot] : 0u, real ? sz[slot] : 0u};
+      // lanes of a warp (of a half-warp when m == 16) share a sub-segment: reduce before the atomics
       const unsigned mask = m >= 32 ? 0xffffffffu : ((tid & 16) ? 0xffff0000u : 0x0000ffffu);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -173,38 +196,173 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
     __syncthreads();
     for (int q = tid; q < nseg; q += kLocalThreads) axis[q] = (unsigned char)widest_axis(bb + 6 * q);
     __syncthreads();
-    for (int i = tid; i < m0; i += kLocalThreads) {
-      const int slot = perm[i];
-      const int a = axis[i / m];
-      key[i] = a == 0 ? sx[slot] : (a == 1 ? sy[slot] : sz[slot]);
-    }
-    __syncthreads();
-    // bitonic sort of (key, perm) inside every sub-segment of size m, ascending.
-    // Pair t of a stage with stride jj is (i, i|jj), i = t with a zero bit inserted
-    // at log2(jj): for jj <= 32 the 32 pairs of a warp stay inside the warp's own
-    // 64-element window.  A stage with jj >= 32 follows one that wrote across
-    // warps (stride 2*jj >= 64) or opens a new merge, so it starts with a block
-    // barrier; stages with jj <= 16 follow warp-local stages and only need a
-    // warp barrier.
-    for (int k = 2; k <= m; k <<= 1) {
-      for (int jj = k >> 1; jj > 0; jj >>= 1) {
-        if (jj >= 32) __syncthreads(); else __syncwarp();
-        for (int t = tid; t < m0 / 2; t += kLocalThreads) {
-          const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-          const int l = i | jj;
-          const bool up = ((i & (m - 1)) & k) == 0;
-          const unsigned ki = key[i], kl = key[l];
-          if ((ki > kl) == up && ki != kl) {
-            key[i] = kl; key[l] = ki;
-            const unsigned short pi = perm[i];
-            perm[i] = perm[l]; perm[l] = pi;
+
+    if (m >= kRadixMin) {
+      // ================= median split by radix select + stable partition =================
+      // 16-bit key: coordinate quantised over the sub-segment's extent; padding = 0xffff
+      for (int i = tid; i < m0; i += kLocalThreads) {
+        const int slot = perm[i];
+        const int sg = i / m;
+        const int a = axis[sg];
+        unsigned k16 = 0xffffu;
+        if (slot < cnt) {
+          const unsigned* q = bb + 6 * sg;
+          const float lo = ord2f(q[a]), hi = ord2f(q[3 + a]);
+          const float x = ord2f(a == 0 ? sx[slot] : (a == 1 ? sy[slot] : sz[slot]));
+          const float scale = hi > lo ? 65534.0f / (hi - lo) : 0.f;
+          k16 = (unsigned)max(0, min(65534, (int)((x - lo) * scale)));
+        }
+        key[i] = k16;
+      }
+      const int target = m / 2;  // the left child takes the `target` smallest keys
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int q = tid; q < nseg * 256; q += kLocalThreads) hist[q] = 0;
+        __syncthreads();
+        for (int i = tid; i < m0; i += kLocalThreads) {
+          const int sg = i / m;
+          const unsigned k16 = key[i];
+          const bool in = pass == 0 || (int)(k16 >> 8) == seg_b1[sg];
+          const unsigned act = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const unsigned bin = pass == 0 ? (k16 >> 8) : (k16 & 255u);
+            const unsigned peers = __match_any_sync(act, bin);
+            if (lane == __ffs(peers) - 1) atomicAdd(&hist[sg * 256 + bin], (unsigned)__popc(peers));
+          }
+        }
+        __syncthreads();
+        // one warp per sub-segment: smallest bin whose cumulative count reaches the target
+        const int w = tid >> 5;
+        if (w < nseg) {
+          const unsigned* h = hist + w * 256;
+          const int want = pass == 0 ? target : target - seg_below[w];
+          int mine[8], sum = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { mine[j] = (int)h[lane * 8 + j]; sum += mine[j]; }
+          int incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+          }
+          const unsigned reach = __ballot_sync(0xffffffffu, incl >= want);
+          const int sel = __ffs(reach) - 1;  // always found: the segment holds m >= want slots
+          if (lane == sel) {
+            int cum = incl - sum, j = 0;
+            for (; j < 7; ++j) {
+              if (cum + mine[j] >= want) break;
+              cum += mine[j];
+            }
+            const int bin = lane * 8 + j;
+            if (pass == 0) {
+              seg_b1[w] = bin;
+              seg_below[w] = cum;
+            } else {
+              seg_kp[w] = (seg_b1[w] << 8) | bin;
+              seg_less[w] = seg_below[w] + cum;
+              seg_eq[w] = mine[j];
+              seg_tie[w] = target - (seg_below[w] + cum);  // ties that still go left (>= 1)
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // stable partition: per-chunk counts -> exclusive offsets inside the sub-segment
+      const int rounds = (m0 + kLocalThreads - 1) / kLocalThreads;
+      int my_rank[kLocal / kLocalThreads];
+      signed char my_side[kLocal / kLocalThreads];  // 0 less, 1 equal, 2 greater
+#pragma unroll
+      for (int r = 0; r < kLocal / kLocalThreads; ++r) {
+        const int i = r * kLocalThreads + tid;
+        my_side[r] = -1;
+        my_rank[r] = 0;
+        if (r < rounds && i < m0) {
+          const int sg = i / m;
+          const int k16 = (int)key[i], kp = seg_kp[sg];
+          const int side = k16 < kp ? 0 : (k16 == kp ? 1 : 2);
+          const unsigned bl = __ballot_sync(0xffffffffu, side == 0);
+          const unsigned be = __ballot_sync(0xffffffffu, side == 1);
+          const unsigned bg = ~(bl | be);
+          const unsigned lt = (1u << lane) - 1u;
+          my_side[r] = (signed char)side;
+          my_rank[r] = __popc((side == 0 ? bl : (side == 1 ? be : bg)) & lt);
+          if (lane == 0) { ch_l[i >> 5] = (unsigned short)__popc(bl); ch_e[i >> 5] = (unsigned short)__popc(be); }
+        }
+      }
+      __syncthreads();
+      if (tid < m0 / 32) {
+        const int per = m / 32, first = (tid / per) * per;
+        int sl = 0, se = 0;
+        for (int c2 = first; c2 < tid; ++c2) { sl += ch_l[c2]; se += ch_e[c2]; }
+        ch_ol[tid] = (unsigned short)sl;
+        ch_oe[tid] = (unsigned short)se;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kLocal / kLocalThreads; ++r) {
+        const int i = r * kLocalThreads + tid;
+        if (my_side[r] >= 0) {
+          const int sg = i / m, ch = i >> 5, base = sg * m;
+          const int ol = ch_ol[ch], oe = ch_oe[ch];
+          int pos;
+          if (my_side[r] == 0) {
+            pos = base + ol + my_rank[r];
+          } else if (my_side[r] == 1) {
+            const int e = oe + my_rank[r], tie = seg_tie[sg];
+            pos = e < tie ? base + seg_less[sg] + e : base + target + (e - tie);
+          } else {
+            const int og = (ch - sg * (m / 32)) * 32 - ol - oe;
+            pos = base + target + (seg_eq[sg] - seg_tie[sg]) + og + my_rank[r];
+          }
+          perm_next[pos] = perm[i];
+        }
+      }
+      __syncthreads();
+      unsigned short* t = perm; perm = perm_next; perm_next = t;
+    } else {
+      // ================= small sub-segments: bitonic sort of (key, perm) ==================
+      for (int i = tid; i < m0; i += kLocalThreads) {
+        const int slot = perm[i];
+        const int a = axis[i / m];
+        key[i] = a == 0 ? sx[slot] : (a == 1 ? sy[slot] : sz[slot]);
+      }
+      // Pair t of a stage with stride jj is (i, i|jj), i = t with a zero bit inserted
+      // at log2(jj): for jj <= 32 the 32 pairs of a warp stay inside the warp's own
+      // 64-element window.  A stage with jj >= 32 follows one that wrote across
+      // warps or opens a new merge, so it starts with a block barrier; stages with
+      // jj <= 16 follow warp-local stages and only need a warp barrier.
+      __syncthreads();
+      for (int k = 2; k <= m; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          if (jj >= 32) __syncthreads(); else __syncwarp();
+          for (int t = tid; t < m0 / 2; t += kLocalThreads) {
+            const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+            const int l = i | jj;
+            const bool up = ((i & (m - 1)) & k) == 0;
+            const unsigned ki = key[i], kl = key[l];
+            if ((ki > kl) == up && ki != kl) {
+              key[i] = kl; key[l] = ki;
+              const unsigned short pi = perm[i];
+              perm[i] = perm[l]; perm[l] = pi;
+            }
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  for (int i = tid; i < cnt; i += kLocalThreads) v[i] = sid[perm[i]];
+  // apply the permutation to the original indices in place: gather, barrier, write
+  uint32_t out[kLocal / kLocalThreads];
+#pragma unroll
+  for (int r = 0; r < kLocal / kLocalThreads; ++r) {
+    const int i = r * kLocalThreads + tid;
+    out[r] = i < cnt ? v[perm[i]] : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kLocal / kLocalThreads; ++r) {
+    const int i = r * kLocalThreads + tid;
+    if (i < cnt) v[i] = out[r];
+  }
 }
 
 }  // namespace
@@ -245,7 +403,8 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
   }
   const int m0 = std::min(span, kLocal);
   const int segs = span / m0;
-  const size_t smem = (size_t)kLocal * 4 * 5 + 6 * (kLocal / 16) * 4 + (size_t)kLocal * 2 + kLocal / 16;
+  const size_t smem = (size_t)kLocal * 4 * 4 + 6 * (kLocal / 16) * 4 + (size_t)kMaxRadixSegs * 256 * 4 +
+                      6 * kMaxRadixSegs * 4 + (size_t)kLocal * 2 * 2 + 4 * kChunks * 2 + kLocal / 16 + 64;
   PGS_CUDA(cudaFuncSetAttribute(kd_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kd_local_kernel<<<dim3(segs, B), kLocalThreads, smem, st>>>(clouds.p, vals_a, span, segs, m0);
   ctx_count_launches(ctx, 1);
