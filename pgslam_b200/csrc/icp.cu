@@ -23,6 +23,12 @@
 #include "knn.cuh"
 #include "solve.cuh"
 
+#ifdef PGS_MATCH_MIN_BLOCKS
+#define PGS_MATCH_BOUNDS __launch_bounds__(128, PGS_MATCH_MIN_BLOCKS)
+#else
+#define PGS_MATCH_BOUNDS __launch_bounds__(128)
+#endif
+
 namespace pgs {
 
 namespace {
@@ -378,7 +384,7 @@ gather_vec3_sorted_kernel(const float4* __restrict__ sorted_pts, int n, const fl
   else out1[j] = src[o];
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void PGS_MATCH_BOUNDS
 match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
   PairState& st = states[blockIdx.y];
   if (!st.active) return;
