@@ -131,6 +131,8 @@ def cpu_reference_run(steps, warmup, sample_pairs=1):
     cfg = ob.config_from_dict(c2_config())
     pairs = gen_pairs(range(1000, 1000 + sample_pairs))
     clouds = [(ob.Cloud(rd), ob.Cloud(rf)) for rd, rf in pairs]
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    ob.lib().orc_set_num_threads(os.cpu_count() or 1)
     threads = ob.lib().orc_num_threads()
     its = []
     for i in range(warmup):
@@ -331,8 +333,8 @@ def main():
                                       "frac": reg_bytes * value / world / 1e9 / peak}
 
     cpu = None
-    if not args.no_cpu_baseline:
-        n = args.cpu_steps or 12
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
+        n = args.cpu_steps or 64  # ~10 s of CPU work on this class of host
         r = cpu_reference_run(n, 1, sample_pairs=min(4, n))
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 

@@ -18,8 +18,8 @@ _LIB = None
 OK, CONVERGENCE_ERROR, TRANSFORMATION_ERROR, INVALID_PARAMETER, INVALID_FIELD = range(5)
 
 F_RANDOM_SAMPLING, F_VOXEL_GRID, F_SURFACE_NORMAL, F_OBSERVATION_DIRECTION = 1, 2, 3, 4
-F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST = 5, 6, 7, 8
-O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST = 1, 2, 3, 4
+F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST, F_BOUNDING_BOX = 5, 6, 7, 8, 9
+O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST, O_SURFACE_NORMAL = 1, 2, 3, 4, 5
 E_POINT_TO_PLANE, E_POINT_TO_PLANE_WITH_COV, E_POINT_TO_POINT = 1, 2, 3
 MAX_MODS = 8
 
@@ -35,7 +35,7 @@ class CCloud(C.Structure):
 
 class CFilter(C.Structure):
     _fields_ = [("type", C.c_int), ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
-                ("i0", C.c_int64), ("i1", C.c_int64)]
+                ("i0", C.c_int64), ("i1", C.c_int64), ("box", C.c_double * 6)]
 
 
 class COutlier(C.Structure):
@@ -106,6 +106,7 @@ def lib():
     L.orc_rigid_transform.argtypes = [cp, _dp]
     L.orc_outlier_weights.argtypes = [C.POINTER(COutlier), C.c_int, _fp, C.c_int64, _fp]
     L.orc_dists_quantile.argtypes = [_fp, C.c_int64, C.c_double, _fp]
+    L.orc_outlier_weights_full.argtypes = [C.POINTER(COutlier), C.c_int, cp, cp, _ip, _fp, C.c_int, _fp]
     L.orc_minimize.argtypes = [C.c_int, C.c_double, cp, cp, _ip, _fp, _fp, C.c_int, C.POINTER(CMinOut)]
     L.orc_overlap.restype = C.c_double
     L.orc_overlap.argtypes = [C.c_int, cp, cp, _ip, _fp, _fp, C.c_int]
@@ -259,6 +260,10 @@ def make_filter(name: str, **p) -> CFilter:
         f.type, f.i0, f.p0 = F_MAX_DIST, int(p.get("dim", -1)), float(p.get("maxDist", 1.0))
     elif name == "MinDistDataPointsFilter":
         f.type, f.i0, f.p0 = F_MIN_DIST, int(p.get("dim", -1)), float(p.get("minDist", 1.0))
+    elif name == "BoundingBoxDataPointsFilter":
+        f.type, f.i0 = F_BOUNDING_BOX, int(p.get("removeInside", 1))
+        for j, (key, dflt) in enumerate((("xMin", -1), ("xMax", 1), ("yMin", -1), ("yMax", 1), ("zMin", -1), ("zMax", 1))):
+            f.box[j] = float(p.get(key, dflt))
     else:
         raise KeyError(name)
     return f
@@ -274,6 +279,8 @@ def make_outlier(name: str, **p) -> COutlier:
         o.type, o.p0 = O_MIN_DIST, float(p.get("minDist", 1.0))
     elif name == "MedianDistOutlierFilter":
         o.type, o.p0 = O_MEDIAN_DIST, float(p.get("factor", 3.0))
+    elif name == "SurfaceNormalOutlierFilter":
+        o.type, o.p0 = O_SURFACE_NORMAL, float(p.get("maxAngle", 1.57))
     else:
         raise KeyError(name)
     return o
@@ -399,6 +406,19 @@ def outlier_weights(outliers, d2):
     d = np.ascontiguousarray(np.asarray(d2, np.float32).T).ravel()
     w = np.empty_like(d)
     st = lib().orc_outlier_weights(arr, len(mods), _f(d), d.size, _f(w))
+    return st, w.reshape(np.asarray(d2).T.shape).T
+
+
+def outlier_weights_full(outliers, reading: Cloud, reference: Cloud, ids, d2):
+    mods = _modlist(outliers)
+    arr = (COutlier * max(1, len(mods)))()
+    for j, (name, p) in enumerate(mods):
+        arr[j] = make_outlier(name, **p)
+    k = np.asarray(d2).shape[0]
+    I = np.ascontiguousarray(np.asarray(ids, np.int32).T).ravel()
+    d = np.ascontiguousarray(np.asarray(d2, np.float32).T).ravel()
+    w = np.empty_like(d)
+    st = lib().orc_outlier_weights_full(arr, len(mods), reading.ptr, reference.ptr, _i(I), _f(d), k, _f(w))
     return st, w.reshape(np.asarray(d2).T.shape).T
 
 

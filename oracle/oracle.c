@@ -884,8 +884,26 @@ static int filter_dist(const orc_filter *f, orc_cloud *c, int is_max) {
   return ORC_OK;
 }
 
+static int filter_bounding_box(const orc_filter *f, orc_cloud *c) {
+  /* BoundingBoxDataPointsFilter [UPSTREAM-RECALLED]: strict inequalities */
+  float lo[3] = {(float)f->box[0], (float)f->box[2], (float)f->box[4]};
+  float hi[3] = {(float)f->box[1], (float)f->box[3], (float)f->box[5]};
+  int remove_inside = (int)f->i0;
+  int64_t *keep = (int64_t *)malloc((size_t)(c->n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = 0; i < c->n; ++i) {
+    const float *p = c->feat + 4 * i;
+    int in = p[0] > lo[0] && p[0] < hi[0] && p[1] > lo[1] && p[1] < hi[1] && p[2] > lo[2] && p[2] < hi[2];
+    if (remove_inside ? !in : in) keep[m++] = i;
+  }
+  cloud_select(c, keep, m);
+  free(keep);
+  return ORC_OK;
+}
+
 int orc_filter_apply(const orc_filter *f, orc_cloud *c) {
   switch (f->type) {
+    case ORC_F_BOUNDING_BOX: return filter_bounding_box(f, c);
     case ORC_F_RANDOM_SAMPLING: return filter_random_sampling(f, c);
     case ORC_F_VOXEL_GRID: return filter_voxel_grid(f, c);
     case ORC_F_SURFACE_NORMAL: return filter_surface_normal(f, c);
@@ -973,6 +991,56 @@ int orc_outlier_weights(const orc_outlier *o, int no, const float *d2, int64_t n
         for (int64_t i = 0; i < nk; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
         break;
       default: return ORC_INVALID_PARAMETER;
+    }
+  }
+  return ORC_OK;
+}
+
+int orc_outlier_weights_full(const orc_outlier *o, int no, const orc_cloud *reading,
+                             const orc_cloud *reference, const int32_t *ids, const float *d2,
+                             int k, float *w) {
+  int64_t nk = reading->n * k;
+  orc_outlier dist_only[ORC_MAX_MODS];
+  int nd = 0, has_sn = 0;
+  for (int f = 0; f < no; ++f) {
+    if (o[f].type == ORC_O_SURFACE_NORMAL) has_sn = 1;
+    else dist_only[nd++] = o[f];
+  }
+  int st;
+  if (nd == 0 && no > 0) {
+    for (int64_t i = 0; i < nk; ++i) w[i] = 1.f;
+    st = ORC_OK;
+  } else {
+    st = orc_outlier_weights(dist_only, nd, d2, nk, w);
+  }
+  if (st || !has_sn) return st;
+  for (int f = 0; f < no; ++f) {
+    if (o[f].type != ORC_O_SURFACE_NORMAL) continue;
+    /* SurfaceNormalOutlierFilter [UPSTREAM-RECALLED]: skipped (weights 1) unless
+     * both clouds carry normals; w = 0 where the unit normals' dot < cos(maxAngle) */
+    if (!reading->normals || !reference->normals) continue;
+    float eps = (float)cos(o[f].p0);
+    for (int64_t i = 0; i < reading->n; ++i) {
+      const float *a = reading->normals + 3 * i;
+      float na = a[0] * a[0];
+      na = na + a[1] * a[1];
+      na = na + a[2] * a[2];
+      na = sqrtf(na);
+      float ax = a[0] / na, ay = a[1] / na, az = a[2] / na;
+      for (int kk = 0; kk < k; ++kk) {
+        size_t m = (size_t)i * k + kk;
+        if (ids[m] < 0) { w[m] = 0.f; continue; }
+        const float *b = reference->normals + 3 * (int64_t)ids[m];
+        float nb = b[0] * b[0];
+        nb = nb + b[1] * b[1];
+        nb = nb + b[2] * b[2];
+        nb = sqrtf(nb);
+        float bx = b[0] / nb, by = b[1] / nb, bz = b[2] / nb;
+        float dot = ax * bx;
+        dot = dot + ay * by;
+        dot = dot + az * bz;
+        w[m] *= (dot < eps) ? 0.f : 1.f;
+      }
     }
   }
   return ORC_OK;
@@ -1402,7 +1470,7 @@ static int icp_loop(const orc_icp_config *cfg, const orc_cloud *readingIn,
     double tk = now_s();
     res->visits += orc_kdtree_knn(tree, step->feat, step->n, k, (float)cfg->max_dist, 1, ids, d2);
     res->time_knn_s += now_s() - tk;
-    st = orc_outlier_weights(cfg->outliers, cfg->n_outliers, d2, step->n * k, w);
+    st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, step, reference, ids, d2, k, w);
     if (st) break;
     st = orc_minimize(cfg->minimizer, cfg->sensor_std_dev, step, reference, ids, d2, w, k, &mo);
     if (st) break;
@@ -1508,7 +1576,7 @@ int orc_probe_overlap(const orc_icp_config *cfg, const orc_cloud *readingIn,
     float *d2 = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     float *w = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     orc_kdtree_knn(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, ids, d2);
-    st = orc_outlier_weights(cfg->outliers, cfg->n_outliers, d2, rd->n * k, w);
+    st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, rd, ref, ids, d2, k, w);
     if (!st) {
       int64_t kept = 0;
       double wsum = 0.0;
@@ -1537,7 +1605,7 @@ int orc_probe_residual(const orc_icp_config *cfg, const orc_cloud *readingIn,
     float *d2 = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     float *w = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     orc_kdtree_knn(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, ids, d2);
-    st = orc_outlier_weights(cfg->outliers, cfg->n_outliers, d2, rd->n * k, w);
+    st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, rd, reference, ids, d2, k, w);
     if (!st) {
       orc_min_out mo;
       st = orc_minimize(cfg->minimizer, cfg->sensor_std_dev, rd, reference, ids, d2, w, k, &mo);

@@ -82,12 +82,14 @@ enum {
   ORC_F_ORIENT_NORMALS = 5,  /* i0 = towardCenter                           */
   ORC_F_SIMPLE_SENSOR_NOISE = 6, /* i0 = sensorType, p0 = gain              */
   ORC_F_MAX_DIST = 7,        /* i0 = dim (-1 radial), p0 = maxDist          */
-  ORC_F_MIN_DIST = 8         /* i0 = dim (-1 radial), p0 = minDist          */
+  ORC_F_MIN_DIST = 8,        /* i0 = dim (-1 radial), p0 = minDist          */
+  ORC_F_BOUNDING_BOX = 9     /* box[6] = xMin,xMax,yMin,yMax,zMin,zMax; i0 = removeInside */
 };
 typedef struct {
   int type;
   double p0, p1, p2;
   int64_t i0, i1;
+  double box[6];
 } orc_filter;
 
 int orc_filter_apply(const orc_filter *f, orc_cloud *c);
@@ -101,7 +103,8 @@ enum {
   ORC_O_TRIMMED_DIST = 1, /* p0 = ratio   */
   ORC_O_MAX_DIST = 2,     /* p0 = maxDist */
   ORC_O_MIN_DIST = 3,     /* p0 = minDist */
-  ORC_O_MEDIAN_DIST = 4   /* p0 = factor  */
+  ORC_O_MEDIAN_DIST = 4,  /* p0 = factor  */
+  ORC_O_SURFACE_NORMAL = 5 /* p0 = maxAngle: needs `normals` on both clouds */
 };
 typedef struct {
   int type;
@@ -111,6 +114,10 @@ typedef struct {
 int orc_outlier_weights(const orc_outlier *o, int no, const float *d2,
                         int64_t nk, float *w);
 int orc_dists_quantile(const float *d2, int64_t nk, double q, float *out);
+/* same, for filters that also look at the clouds (SurfaceNormalOutlierFilter) */
+int orc_outlier_weights_full(const orc_outlier *o, int no, const orc_cloud *reading,
+                             const orc_cloud *reference, const int32_t *ids,
+                             const float *d2, int k, float *w);
 
 /* ---- error minimizers (A.4 – A.7) -------------------------------------- */
 enum {

@@ -459,15 +459,17 @@ pgs_status pgs_outliers_append(pgs_outliers* o, const char* name, const char* co
 pgs_status pgs_outliers_compute(pgs_outliers* o, const pgs_cloud* reading, const pgs_cloud* reference,
                                 const int32_t* ids, const float* dists2, int k, float* weights, int on_device) {
   PGS_API_BEGIN
-  (void)reference;
-  (void)ids;
+  reading->c->wait_ready();
+  reference->c->wait_ready();
   const int64_t nk = reading->c->n * k;
   if (on_device) {
-    outlier_weights_device(o->ctx, o->mods, dists2, nk, weights);
+    outlier_weights_device(o->ctx, o->mods, dists2, nk, weights, reading->c.get(), reference->c.get(), ids, k);
   } else {
     DBuf<float> dd(o->ctx, (size_t)nk), dw(o->ctx, (size_t)nk);
+    DBuf<int32_t> di(o->ctx, (size_t)nk);
     copy_in(o->ctx, dd.p, dists2, (size_t)nk * sizeof(float), 0);
-    outlier_weights_device(o->ctx, o->mods, dd.p, nk, dw.p);
+    copy_in(o->ctx, di.p, ids, (size_t)nk * sizeof(int32_t), 0);
+    outlier_weights_device(o->ctx, o->mods, dd.p, nk, dw.p, reading->c.get(), reference->c.get(), di.p, k);
     copy_out(o->ctx, weights, dw.p, (size_t)nk * sizeof(float), 0);
   }
   PGS_API_END(o->ctx)
@@ -615,7 +617,7 @@ pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const p
   DBuf<int32_t> ids(ctx, nk);
   DBuf<float> d2(ctx, nk), w(ctx, nk);
   matcher_find(&m, *rd, ids.p, d2.p);
-  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p);
+  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p, rd.get(), ref.get(), ids.p, k);
   double kept = 0, wsum = 0;
   weights_ratio_device(ctx, d2.p, w.p, (int64_t)nk, &kept, &wsum);
   if (!(kept > 0)) throw Error(PGS_CONVERGENCE_ERROR, "no point to minimize");
@@ -642,7 +644,7 @@ pgs_status pgs_icp_probe_residual(pgs_icp* icp, const pgs_cloud* reading, const 
   DBuf<int32_t> ids(ctx, nk);
   DBuf<float> d2(ctx, nk), w(ctx, nk);
   matcher_find(&m, *rd, ids.p, d2.p);
-  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p);
+  outlier_weights_device(ctx, icp->cfg.outlier_filters, d2.p, (int64_t)nk, w.p, rd.get(), reference->c.get(), ids.p, k);
   pgs_min_result mr;
   minimize_device(ctx, icp->cfg.minimizer, *rd, *reference->c, ids.p, d2.p, w.p, k, &mr);
   *residual = mr.residual;

@@ -114,6 +114,16 @@ dist_keep_kernel(const float4* __restrict__ feat, int* __restrict__ keep, int n,
   keep[i] = is_max ? (v < l) : (v > l);
 }
 
+__global__ void __launch_bounds__(256)
+box_keep_kernel(const float4* __restrict__ feat, int* __restrict__ keep, int n, float x0, float x1, float y0,
+                float y1, float z0, float z1, int remove_inside) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = feat[i];
+  bool in = p.x > x0 && p.x < x1 && p.y > y0 && p.y < y1 && p.z > z0 && p.z < z1;
+  keep[i] = remove_inside ? !in : in;
+}
+
 // ---------------------------------------------------------------------------
 // SurfaceNormalDataPointsFilter: per-point covariance of the kNN set, 3x3
 // eigen-decomposition (fp64 cyclic Jacobi), smallest-eigenvalue eigenvector.
@@ -457,6 +467,15 @@ void apply_filter(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
       if (!n) continue;
       DBuf<int> keep(ctx, n);
       random_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(keep.p, n, (uint64_t)m.integer("seed"), (float)m.real("prob"));
+      ctx_count_launches(ctx, 1);
+      compact_cloud(c, keep.p);
+      continue;
+    } else if (name == "BoundingBoxDataPointsFilter") {
+      if (!n) continue;
+      DBuf<int> keep(ctx, n);
+      box_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, keep.p, n, (float)m.real("xMin"), (float)m.real("xMax"),
+                                                       (float)m.real("yMin"), (float)m.real("yMax"), (float)m.real("zMin"),
+                                                       (float)m.real("zMax"), m.flag("removeInside") ? 1 : 0);
       ctx_count_launches(ctx, 1);
       compact_cloud(c, keep.p);
       continue;

@@ -119,6 +119,17 @@ __device__ __forceinline__ void accumulate_cov(double* acc2, const float3 pf, co
     }
 }
 
+// SurfaceNormalOutlierFilter: weight 0 iff the unit normals' dot product is below
+// cos(maxAngle); fp32, fixed order (NaN from a zero normal compares false -> kept)
+__device__ __forceinline__ bool sn_reject(float ax, float ay, float az, float bx, float by, float bz, float eps) {
+  float na = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+  float nb = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(bx, bx), __fmul_rn(by, by)), __fmul_rn(bz, bz)));
+  float ux = __fdiv_rn(ax, na), uy = __fdiv_rn(ay, na), uz = __fdiv_rn(az, na);
+  float vx = __fdiv_rn(bx, nb), vy = __fdiv_rn(by, nb), vz = __fdiv_rn(bz, nb);
+  float dot = __fadd_rn(__fadd_rn(__fmul_rn(ux, vx), __fmul_rn(uy, vy)), __fmul_rn(uz, vz));
+  return dot < eps;
+}
+
 __device__ void xf_from_T_dev(const double* T, Xf& x) {
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 4; ++c) x.m[r * 4 + c] = (float)T[c * 4 + r];
@@ -541,6 +552,12 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
     bool use = pos >= 0 && d < kInfF;
     if (P.has_outliers) use = use && d <= hi && d >= lo;
     if (!use) continue;
+    if (P.has_sn && v.rd_normals && v.ref_normals) {
+      float4 a = v.rd_normals[i];
+      float3 ar = rot_rn(T, a.x, a.y, a.z);
+      float4 b = v.ref_normals[pos];
+      if (sn_reject(ar.x, ar.y, ar.z, b.x, b.y, b.z, P.sn_eps)) continue;
+    }
     float4 r = v.reading[i];
     float3 p = xform_rn(T, r.x, r.y, r.z);
     float4 q = v.tree.pts[pos];
@@ -615,6 +632,12 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
     bool use = pos >= 0 && d < kInfF;
     if (P.has_outliers) use = use && d <= hi && d >= lo;
     if (!use) continue;
+    if (P.has_sn && v.rd_normals && v.ref_normals) {
+      float4 a = v.rd_normals[i];
+      float3 ar = rot_rn(T, a.x, a.y, a.z);
+      float4 b = v.ref_normals[pos];
+      if (sn_reject(ar.x, ar.y, ar.z, b.x, b.y, b.z, P.sn_eps)) continue;
+    }
     float4 r = v.reading[i];
     float3 p = xform_rn(T, r.x, r.y, r.z);
     float4 q = v.tree.pts[pos];
@@ -875,6 +898,8 @@ void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p) {
   p->n_quant = 0;
   p->fixed_hi = kInfF;
   p->fixed_lo = -kInfF;
+  p->has_sn = 0;
+  p->sn_eps = -2.f;
   for (auto& f : filters) {
     if (f.name == "NullOutlierFilter") {
       // weight 1 for everything; combined with others it is a no-op.  Alone it
@@ -895,6 +920,10 @@ void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p) {
     } else if (f.name == "MinDistOutlierFilter") {
       float m = (float)f.real("minDist");
       p->fixed_lo = std::max(p->fixed_lo, m * m);
+    } else if (f.name == "SurfaceNormalOutlierFilter") {
+      // several of them: the largest cosine is the binding one
+      p->has_sn = 1;
+      p->sn_eps = std::max(p->sn_eps, (float)std::cos(f.real("maxAngle")));
     } else {
       throw Error(PGS_INVALID_ELEMENT, "OutlierFilter " + f.name + " has no device implementation");
     }
@@ -1160,13 +1189,17 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     v.ref_normals = refs[p]->has_normals ? refs[p]->normals_sorted.p : nullptr;
     const Desc* nrm = rdp[p]->find("normals");
     const Desc* noise = rdp[p]->find("simpleSensorNoise");
-    if (nrm && noise && nr > 0 && prm.minimizer != MIN_P2POINT) {
+    const bool for_overlap = nrm && noise && prm.minimizer != MIN_P2POINT;
+    if (nrm && nr > 0 && (for_overlap || prm.has_sn)) {
       rdn[p].reset(ctx, (size_t)nr);
-      rdnoise[p].reset(ctx, (size_t)nr);
       gather_vec3_sorted_kernel<<<ceil_div(nr, 256), 256, 0, s>>>(rd_sorted[p]->pts.p, nr, nrm->data.p, 3, rdn[p].p, nullptr);
-      gather_vec3_sorted_kernel<<<ceil_div(nr, 256), 256, 0, s>>>(rd_sorted[p]->pts.p, nr, noise->data.p, 1, nullptr, rdnoise[p].p);
-      ctx_count_launches(ctx, 2);
+      ctx_count_launches(ctx, 1);
       v.rd_normals = rdn[p].p;
+    }
+    if (for_overlap && nr > 0) {
+      rdnoise[p].reset(ctx, (size_t)nr);
+      gather_vec3_sorted_kernel<<<ceil_div(nr, 256), 256, 0, s>>>(rd_sorted[p]->pts.p, nr, noise->data.p, 1, nullptr, rdnoise[p].p);
+      ctx_count_launches(ctx, 1);
       v.rd_noise = rdnoise[p].p;
     }
     v.match_pos = mpos[p].p;
@@ -1224,7 +1257,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
 
   // ---- covariance / overlap / final pose -------------------------------------------
   bool need_final = prm.minimizer == MIN_P2PLANE_COV;
-  for (int p = 0; p < P; ++p) need_final = need_final || hv[p].rd_normals != nullptr;
+  for (int p = 0; p < P; ++p) need_final = need_final || hv[p].rd_noise != nullptr;
   if (need_final) {
     final_accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm);
     ctx_count_launches(ctx, 1);
@@ -1280,7 +1313,23 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
 // ---------------------------------------------------------------------------
 // fine-grained modules
 // ---------------------------------------------------------------------------
-void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const float* d_d2, int64_t nk, float* d_w) {
+namespace {
+__global__ void __launch_bounds__(256)
+sn_weights_kernel(const float* __restrict__ rd_normals, const float* __restrict__ ref_normals,
+                  const int32_t* __restrict__ ids, int64_t nk, int k, float eps, float* __restrict__ w) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nk) return;
+  const int id = ids[m];
+  if (id < 0) { w[m] = 0.f; return; }
+  const int64_t i = m / k;
+  if (sn_reject(rd_normals[3 * i], rd_normals[3 * i + 1], rd_normals[3 * i + 2], ref_normals[3 * (int64_t)id],
+                ref_normals[3 * (int64_t)id + 1], ref_normals[3 * (int64_t)id + 2], eps))
+    w[m] = 0.f;
+}
+}  // namespace
+
+void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const float* d_d2, int64_t nk, float* d_w,
+                            const Cloud* reading, const Cloud* reference, const int32_t* d_ids, int k) {
   IcpParams p;
   std::memset(&p, 0, sizeof(p));
   outlier_limits_params(filters, &p);
@@ -1304,8 +1353,20 @@ void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const 
     }
   }
   if (nk > 0) {
-    weights_kernel<<<ceil_div(nk, 256), 256, 0, ctx->stream>>>(d_d2, nk, p.has_outliers, lo, hi, d_w);
+    // a chain made only of SurfaceNormal filters starts from weights 1 (not from "dist != inf")
+    bool only_sn = p.has_sn;
+    for (auto& f : filters) only_sn = only_sn && f.name == "SurfaceNormalOutlierFilter";
+    weights_kernel<<<ceil_div(nk, 256), 256, 0, ctx->stream>>>(d_d2, nk, p.has_outliers, only_sn ? -kInfF : lo,
+                                                               only_sn ? kInfF : hi, d_w);
     ctx_count_launches(ctx, 1);
+    if (p.has_sn && reading && reference && d_ids) {
+      const Desc* a = reading->find("normals");
+      const Desc* b = reference->find("normals");
+      if (a && b) {  // "surface normals not available: skipping filtering" otherwise
+        sn_weights_kernel<<<ceil_div(nk, 256), 256, 0, ctx->stream>>>(a->data.p, b->data.p, d_ids, nk, k, p.sn_eps, d_w);
+        ctx_count_launches(ctx, 1);
+      }
+    }
   }
   PGS_LAUNCH_CHECK();
 }

@@ -36,6 +36,8 @@ struct IcpParams {
   float fixed_hi, fixed_lo;  // MaxDist^2 / MinDist^2 limits
   float max_r2;        // matcher maxDist^2
   int hard_iteration_cap;
+  int has_sn;          // SurfaceNormalOutlierFilter present
+  float sn_eps;        // cos(maxAngle)
 };
 
 struct PairState {
@@ -114,7 +116,9 @@ class IcpEngine {
 IcpParams params_from_chain(const ChainConfig& cfg);
 void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p);
 // OutlierFilters::compute on device arrays (k x n dists) -> weights
-void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const float* d_d2, int64_t nk, float* d_w);
+void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const float* d_d2, int64_t nk, float* d_w,
+                            const Cloud* reading = nullptr, const Cloud* reference = nullptr,
+                            const int32_t* d_ids = nullptr, int k = 1);
 // ErrorElements + ErrorMinimizer::compute on explicit matches
 void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, const Cloud& reference,
                      const int32_t* d_ids, const float* d_d2, const float* d_w, int k, pgs_min_result* out);

@@ -62,6 +62,11 @@ const std::vector<ModuleDoc>& registry() {
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"maxDist", "", "1", NINF, INF, 'f'}}},
       {Kind::DataPointsFilter, "MinDistDataPointsFilter",
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"minDist", "", "1", NINF, INF, 'f'}}},
+      {Kind::DataPointsFilter, "BoundingBoxDataPointsFilter",
+       {{"xMin", "", "-1", NINF, INF, 'f'}, {"xMax", "", "1", NINF, INF, 'f'},
+        {"yMin", "", "-1", NINF, INF, 'f'}, {"yMax", "", "1", NINF, INF, 'f'},
+        {"zMin", "", "-1", NINF, INF, 'f'}, {"zMax", "", "1", NINF, INF, 'f'},
+        {"removeInside", "remove the points inside (1) or outside (0) the box", "1", "0", "1", 'u'}}},
       // ---- Matcher (A8, A9) ----------------------------------------------
       {Kind::Matcher, "KDTreeMatcher",
        {{"knn", "number of nearest neighbours", "1", "1", IMAX, 'i'},
@@ -75,6 +80,8 @@ const std::vector<ModuleDoc>& registry() {
       {Kind::OutlierFilter, "MaxDistOutlierFilter", {{"maxDist", "", "1", "0.0000001", INF, 'f'}}},
       {Kind::OutlierFilter, "MinDistOutlierFilter", {{"minDist", "", "1", "0.0000001", INF, 'f'}}},
       {Kind::OutlierFilter, "MedianDistOutlierFilter", {{"factor", "", "3", "0.0000001", INF, 'f'}}},
+      {Kind::OutlierFilter, "SurfaceNormalOutlierFilter",
+       {{"maxAngle", "max angle (rad) between the normals of a matched pair", "1.57", "0.0", "3.1416", 'f'}}},
       // ---- ErrorMinimizers (A12, A12d, A13) ------------------------------
       {Kind::ErrorMinimizer, "PointToPlaneErrorMinimizer",
        {{"force2D", "", "0", "0", "1", 'u'}, {"force4DOF", "", "0", "0", "1", 'u'}}},

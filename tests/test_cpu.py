@@ -61,6 +61,9 @@ def test_config_check_accepts_the_baseline_chains():
         assert pm.check_config(util.to_yaml(cfg)) >= 5
     assert pm.check_config(util.to_yaml(util.INPUT_FILTERS), chain=False) == 4
     assert pm.check_config("", chain=False) == 0
+    assert pm.check_config("- BoundingBoxDataPointsFilter: {xMin: -5, xMax: 5, removeInside: 0}\n", chain=False) == 1
+    assert pm.check_config(util.to_yaml(dict(util.C2, outlierFilters=[
+        {"TrimmedDistOutlierFilter": {"ratio": 0.9}}, {"SurfaceNormalOutlierFilter": {"maxAngle": 0.5}}]))) >= 6
 
 
 def test_config_check_block_and_flow_yaml_styles():

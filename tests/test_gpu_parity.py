@@ -156,6 +156,8 @@ def test_voxel_grid_bit_exact(pm, pair120k, centroid):
     ("RandomSamplingDataPointsFilter", {"prob": 0.6, "seed": 7}),
     ("MaxDistDataPointsFilter", {"dim": -1, "maxDist": 20.0}),
     ("MinDistDataPointsFilter", {"dim": 0, "minDist": 1.5}),
+    ("BoundingBoxDataPointsFilter", {"xMin": -8, "xMax": 12, "yMin": -6, "yMax": 5, "zMin": -3, "zMax": 0.5, "removeInside": 0}),
+    ("BoundingBoxDataPointsFilter", {"xMin": -8, "xMax": 12, "yMin": -6, "yMax": 5, "zMin": -3, "zMax": 0.5, "removeInside": 1}),
 ])
 def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
     rd, _, _ = pair30k
@@ -613,3 +615,41 @@ def test_two_host_threads_two_contexts(pm):
     for i in range(2):
         assert out[i] is not None and out[i][1] == serial[i][1]
         assert np.array_equal(out[i][0], serial[i][0])
+
+
+# ------------------------------------------------ SurfaceNormalOutlierFilter (breadth row F4) ---
+def test_surface_normal_outlier_filter_module_and_fused(pm, pair30k):
+    rd, rf, _ = pair30k
+    ord_, orf = ob.Cloud(rd), ob.Cloud(rf)
+    for oc in (ord_, orf):
+        for it in util.INPUT_FILTERS[:3]:
+            (name, p), = ob._modlist([it])
+            ob.apply_filter(oc, name, **p)
+    rdd, rfd = ord_.descriptors(), orf.descriptors()
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    chain = [{"TrimmedDistOutlierFilter": {"ratio": 0.9}}, {"SurfaceNormalOutlierFilter": {"maxAngle": 0.35}}]
+    o = pm.OutlierFilters()
+    for it in chain:
+        (name, p), = ob._modlist([it])
+        o.append(name, p)
+    got = o.compute(pm.DataPoints(rd, rdd), pm.DataPoints(rf, rfd), pm.Matches(ids, d2))
+    st, want = ob.outlier_weights_full(chain, ord_, orf, ids, d2)
+    assert st == 0 and np.array_equal(got, want)
+    assert 0.3 < want.mean() < 0.9  # the normal test rejects a real share of the matches
+    # only the normal filter, and clouds without normals (filter is skipped, weights stay 1)
+    o2 = pm.OutlierFilters()
+    o2.append("SurfaceNormalOutlierFilter", {"maxAngle": 0.35})
+    got2 = o2.compute(pm.DataPoints(rd, rdd), pm.DataPoints(rf, rfd), pm.Matches(ids, d2))
+    st, want2 = ob.outlier_weights_full(chain[1:], ord_, orf, ids, d2)
+    assert np.array_equal(got2, want2)
+    got3 = o2.compute(pm.DataPoints(rd), pm.DataPoints(rf), pm.Matches(ids, d2))
+    assert (got3 == 1).all()
+    # inside the fused loop
+    cfg = dict(util.C2, referenceDataPointsFilters=[], outlierFilters=chain)
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(cfg))
+    T = icp(pm.DataPoints(rd, rdd), pm.DataPoints(rf, rfd))
+    want = ob.icp_run(cfg, ord_, orf)
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
