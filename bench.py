@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -270,11 +270,13 @@ def main():
             ms = float(t.item())
         return ms, out
 
-    for _ in range(args.warmup):
-        step_resident()
+    # clocks are sampled from the warm-up steps on (same load as the timed steps): the
+    # timed region alone is ~100 ms, too short for more than a sample or two
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
     launches0 = ctx.launch_count
     ctx.set_profiling(True)
     ms, res = timed(step_resident, args.steps)
