@@ -653,3 +653,112 @@ def test_surface_normal_outlier_filter_module_and_fused(pm, pair30k):
     assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
     util.assert_pose_close(T, want["T"])
     assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+
+
+# ------------------------------------------------------------------ edge cases ---
+def _status_of(pm, fn):
+    try:
+        fn()
+        return 0
+    except pm.PointMatcherError as e:
+        return e.status
+
+
+@pytest.mark.parametrize("n_ref,n_rd", [(1, 5), (3, 1), (7, 7), (9, 40), (100, 3)])
+def test_icp_tiny_clouds_match_the_oracle(pm, n_ref, n_rd):
+    g = np.random.default_rng(n_ref * 100 + n_rd)
+    rf = np.ones((4, n_ref), np.float32)
+    rf[:3] = g.normal(size=(3, n_ref)).astype(np.float32)
+    rd = np.ones((4, n_rd), np.float32)
+    rd[:3] = (g.normal(size=(3, n_rd)) + 0.05).astype(np.float32)
+    cfg = dict(util.C1, outlierFilters=[])
+    want = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf))
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(cfg))
+    st = _status_of(pm, lambda: icp(pm.DataPoints(rd), pm.DataPoints(rf)))
+    assert st == want["status"]
+    assert icp.last["iterations"] == want["iterations"]
+    if st == 0:
+        np.testing.assert_allclose(icp.last["T"], want["T"], atol=1e-9)
+
+
+def test_icp_empty_clouds_are_convergence_errors(pm, pair30k):
+    rd, rf, _ = pair30k
+    empty = np.ones((4, 0), np.float32)
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(util.C1))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(empty), pm.DataPoints(rf))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(empty))
+    # filters and the matcher accept empty clouds
+    dp = pm.DataPoints(empty)
+    pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS[:1])).apply(dp)
+    assert dp.getNbPoints() == 0
+    m = pm.Matcher("KDTreeMatcher", {"knn": 2})
+    m.init(pm.DataPoints(rf))
+    assert m.findClosests(pm.DataPoints(empty)).ids.shape == (2, 0)
+
+
+def test_icp_with_matcher_max_dist_and_filter_chain(pm, pair30k):
+    """maxDist on the matcher leaves unmatched points (id -1, dist inf) that every later
+    stage has to skip the same way; several outlier filters multiply."""
+    rd, rf, _ = pair30k
+    cfg = dict(util.C2, matcher={"KDTreeMatcher": {"knn": 1, "maxDist": 0.35}},
+               outlierFilters=[{"MedianDistOutlierFilter": {"factor": 4}}, {"MaxDistOutlierFilter": {"maxDist": 0.3}},
+                               {"MinDistOutlierFilter": {"minDist": 0.001}}])
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["point_used_ratio"] == pytest.approx(want["point_used_ratio"], rel=1e-12)
+    assert icp.last["point_used_ratio"] < 0.9
+    # a radius so small that nothing matches: "no outlier to filter"
+    cfg2 = dict(util.C2, matcher={"KDTreeMatcher": {"knn": 1, "maxDist": 1e-7}})
+    icp.loadFromYaml(util.to_yaml(cfg2))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    assert ob.icp_run(cfg2, ob.Cloud(rd), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+    # ... and without outlier filters: "no point to minimize"
+    cfg3 = dict(cfg2, outlierFilters=[])
+    icp.loadFromYaml(util.to_yaml(cfg3))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    assert ob.icp_run(cfg3, ob.Cloud(rd), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+
+
+def test_batch_with_failing_and_ragged_pairs(pm, pair30k):
+    rd, rf, _ = pair30k
+    small = synth.scan_pair(9, beams=16, az_steps=64)
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    rds = [pm.DataPoints(rd), pm.DataPoints(rf), pm.DataPoints(small[0])]
+    rfs = [pm.DataPoints(rf), pm.DataPoints(rf), pm.DataPoints(small[1])]  # pair 1: identical clouds
+    res = icp.compute_batch(rds, rfs)
+    assert [r["status"] for r in res] == [0, pm.CONVERGENCE_ERROR, 0]
+    for i in (0, 2):
+        want = ob.icp_run(util.C2, ob.Cloud([rd, None, small[0]][i]), ob.Cloud([rf, None, small[1]][i]))
+        assert res[i]["iterations"] == want["iterations"]
+        util.assert_pose_close(res[i]["T"], want["T"])
+
+
+def test_planar_scene_takes_the_rank_deficient_solve(pm):
+    """A single plane constrains 3 of 6 DOF: the normal equations are singular and both
+    sides must fall back to the minimum-norm solution (A.5)."""
+    g = np.random.default_rng(4)
+    n = 5000
+    rf = np.ones((4, n), np.float32)
+    rf[0] = g.uniform(-5, 5, n)
+    rf[1] = g.uniform(-5, 5, n)
+    rf[2] = 0.0
+    T = synth.pose_matrix([0.0, 0.0, 0.07], 0.0, 0.01, -0.008)
+    rd = (np.linalg.inv(T) @ rf.astype(np.float64)).astype(np.float32)
+    nrm = np.zeros((3, n), np.float32)
+    nrm[2] = 1.0
+    cfg = dict(util.C2, referenceDataPointsFilters=[], outlierFilters=[])
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(cfg))
+    Tg = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    want = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf, {"normals": nrm}))
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(Tg, want["T"], 1e-7, 1e-7)
+    assert abs(Tg[2, 3] - 0.07) < 1e-3  # the constrained DOF is recovered
