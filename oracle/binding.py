@@ -59,7 +59,8 @@ class CIcpConfig(C.Structure):
                 ("max_iterations", C.c_int),
                 ("has_differential", C.c_int), ("min_diff_rot", C.c_double),
                 ("min_diff_trans", C.c_double), ("smooth_length", C.c_int),
-                ("has_bound", C.c_int), ("max_rot_norm", C.c_double), ("max_trans_norm", C.c_double)]
+                ("has_bound", C.c_int), ("max_rot_norm", C.c_double), ("max_trans_norm", C.c_double),
+                ("force_mode", C.c_int)]
 
 
 class CIcpResult(C.Structure):
@@ -108,6 +109,7 @@ def lib():
     L.orc_dists_quantile.argtypes = [_fp, C.c_int64, C.c_double, _fp]
     L.orc_outlier_weights_full.argtypes = [C.POINTER(COutlier), C.c_int, cp, cp, _ip, _fp, C.c_int, _fp]
     L.orc_minimize.argtypes = [C.c_int, C.c_double, cp, cp, _ip, _fp, _fp, C.c_int, C.POINTER(CMinOut)]
+    L.orc_minimize_ex.argtypes = [C.c_int, C.c_int, C.c_double, cp, cp, _ip, _fp, _fp, C.c_int, C.POINTER(CMinOut)]
     L.orc_overlap.restype = C.c_double
     L.orc_overlap.argtypes = [C.c_int, cp, cp, _ip, _fp, _fp, C.c_int]
     L.orc_eig3_sym.argtypes = [_dp, _dp, _dp]
@@ -338,6 +340,7 @@ def config_from_dict(cfg: dict) -> CIcpConfig:
                        "PointToPlaneWithCovErrorMinimizer": E_POINT_TO_PLANE_WITH_COV,
                        "PointToPointErrorMinimizer": E_POINT_TO_POINT}[name]
         c.sensor_std_dev = float(p.get("sensorStdDev", 0.01))
+        c.force_mode = 1 if int(p.get("force2D", 0)) else (2 if int(p.get("force4DOF", 0)) else 0)
     if "transformationCheckers" in cfg:
         c.max_iterations, c.has_differential, c.has_bound = 0, 0, 0
         for name, p in _modlist(cfg["transformationCheckers"]):
@@ -422,13 +425,13 @@ def outlier_weights_full(outliers, reading: Cloud, reference: Cloud, ids, d2):
     return st, w.reshape(np.asarray(d2).T.shape).T
 
 
-def minimize(kind, reading: Cloud, reference: Cloud, ids, d2, w, sensor_std_dev=0.01):
+def minimize(kind, reading: Cloud, reference: Cloud, ids, d2, w, sensor_std_dev=0.01, force_mode=0):
     k = ids.shape[0]
     I = np.ascontiguousarray(np.asarray(ids, np.int32).T).ravel()
     D = np.ascontiguousarray(np.asarray(d2, np.float32).T).ravel()
     W = np.ascontiguousarray(np.asarray(w, np.float32).T).ravel()
     o = CMinOut()
-    st = lib().orc_minimize(kind, sensor_std_dev, reading.ptr, reference.ptr, _i(I), _f(D), _f(W), k, C.byref(o))
+    st = lib().orc_minimize_ex(kind, force_mode, sensor_std_dev, reading.ptr, reference.ptr, _i(I), _f(D), _f(W), k, C.byref(o))
     return st, dict(T=np.array(o.T).reshape(4, 4).T.copy(), cov=np.array(o.cov).reshape(6, 6).T.copy(),
                     A=np.array(o.A).reshape(6, 6).T.copy(), b=np.array(o.b), kept=o.kept,
                     point_used_ratio=o.point_used_ratio,

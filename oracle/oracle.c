@@ -502,57 +502,59 @@ void orc_eig3_sym(const double *A, double *w, double *V) {
 /* A x = b, A symmetric PSD 6x6.  Cholesky when well conditioned, else the
  * minimum-norm solution through the eigen-decomposition (A.5's
  * solvePossiblyUnderdeterminedLinearSystem restated).  Returns rank.        */
-int orc_solve6(const double *A, const double *b, double *x) {
+static int solve_n(int n, const double *A, const double *b, double *x) {
   double L[36];
   double maxd = 0.0;
-  for (int i = 0; i < 6; ++i)
-    if (A[i * 6 + i] > maxd) maxd = A[i * 6 + i];
+  for (int i = 0; i < n; ++i)
+    if (A[i * n + i] > maxd) maxd = A[i * n + i];
   int ok = maxd > 0.0;
   memset(L, 0, sizeof(L));
-  for (int j = 0; j < 6 && ok; ++j) {
-    double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= L[k * 6 + j] * L[k * 6 + j];
+  for (int j = 0; j < n && ok; ++j) {
+    double d = A[j * n + j];
+    for (int k = 0; k < j; ++k) d -= L[k * n + j] * L[k * n + j];
     if (!(d > 1e-12 * maxd)) { ok = 0; break; }
     double ljj = sqrt(d);
-    L[j * 6 + j] = ljj;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[j * 6 + i];
-      for (int k = 0; k < j; ++k) s -= L[k * 6 + i] * L[k * 6 + j];
-      L[j * 6 + i] = s / ljj;
+    L[j * n + j] = ljj;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[j * n + i];
+      for (int k = 0; k < j; ++k) s -= L[k * n + i] * L[k * n + j];
+      L[j * n + i] = s / ljj;
     }
   }
   if (ok) {
     double y[6];
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < n; ++i) {
       double s = b[i];
-      for (int k = 0; k < i; ++k) s -= L[k * 6 + i] * y[k];
-      y[i] = s / L[i * 6 + i];
+      for (int k = 0; k < i; ++k) s -= L[k * n + i] * y[k];
+      y[i] = s / L[i * n + i];
     }
-    for (int i = 5; i >= 0; --i) {
+    for (int i = n - 1; i >= 0; --i) {
       double s = y[i];
-      for (int k = i + 1; k < 6; ++k) s -= L[i * 6 + k] * x[k];
-      x[i] = s / L[i * 6 + i];
+      for (int k = i + 1; k < n; ++k) s -= L[i * n + k] * x[k];
+      x[i] = s / L[i * n + i];
     }
-    return 6;
+    return n;
   }
   double B[36], w[6], V[36];
-  memcpy(B, A, sizeof(B));
-  jacobi_sym(6, B, w, V);
+  memcpy(B, A, sizeof(double) * n * n);
+  jacobi_sym(n, B, w, V);
   double wmax = 0.0;
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < n; ++i)
     if (fabs(w[i]) > wmax) wmax = fabs(w[i]);
-  for (int i = 0; i < 6; ++i) x[i] = 0.0;
+  for (int i = 0; i < n; ++i) x[i] = 0.0;
   int rank = 0;
-  for (int e = 0; e < 6; ++e) {
+  for (int e = 0; e < n; ++e) {
     if (!(w[e] > 1e-12 * wmax)) continue;
     ++rank;
     double vb = 0.0;
-    for (int i = 0; i < 6; ++i) vb += V[e * 6 + i] * b[i];
+    for (int i = 0; i < n; ++i) vb += V[e * n + i] * b[i];
     vb = vb / w[e];
-    for (int i = 0; i < 6; ++i) x[i] += vb * V[e * 6 + i];
+    for (int i = 0; i < n; ++i) x[i] += vb * V[e * n + i];
   }
   return rank;
 }
+
+int orc_solve6(const double *A, const double *b, double *x) { return solve_n(6, A, b, x); }
 
 /* 3x3 SVD M = U diag(S) V^T through the eigen-decomposition of M^T M with a
  * Gram–Schmidt completion of U; singular values sorted descending.          */
@@ -1075,11 +1077,33 @@ static void inv6_sym(const double *H, double *Hi) {
 int orc_minimize(int type, double sensor_std_dev, const orc_cloud *reading,
                  const orc_cloud *reference, const int32_t *ids, const float *d2,
                  const float *w, int k, orc_min_out *out) {
+  return orc_minimize_ex(type, ORC_FORCE_NONE, sensor_std_dev, reading, reference, ids, d2, w, k, out);
+}
+
+/* PointToPlaneErrorMinimizer force2D / force4DOF (A.5, upstream
+ * ErrorMinimizers/PointToPlane.cpp compute_in_place [UPSTREAM-RECALLED]):
+ *   force2D   : features and normals cut to x,y; F = [x*ny - y*nx; nx; ny];
+ *               e = dx*nx + dy*ny; unknowns [theta, tx, ty]; Rotation2D(theta)
+ *               written into the top-left of a 4x4 identity.
+ *   force4DOF : F = [(Gamma p).n; nx; ny; nz] with Gamma p = (-y, x, 0);
+ *               e = d.n in 3-D; unknowns [yaw, tx, ty, tz]; AngleAxis(yaw, Z). */
+static void yaw_to_T(double th, double tx, double ty, double tz, double *T) {
+  m4_identity(T);
+  double c = cos(th), s = sin(th);
+  T[0] = c; T[4] = -s;
+  T[1] = s; T[5] = c;
+  T[12] = tx; T[13] = ty; T[14] = tz;
+}
+
+int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_cloud *reading,
+                    const orc_cloud *reference, const int32_t *ids, const float *d2,
+                    const float *w, int k, orc_min_out *out) {
   memset(out, 0, sizeof(*out));
   m4_identity(out->T);
   int64_t nr = reading->n;
   int p2plane = (type == ORC_E_POINT_TO_PLANE || type == ORC_E_POINT_TO_PLANE_WITH_COV);
   if (p2plane && !reference->normals) return ORC_INVALID_FIELD;
+  if (force_mode != ORC_FORCE_NONE && type != ORC_E_POINT_TO_PLANE) return ORC_INVALID_PARAMETER;
   /* ErrorElements (A.4) */
   int64_t kept = 0;
   double wsum = 0.0;
@@ -1093,6 +1117,42 @@ int orc_minimize(int type, double sensor_std_dev, const orc_cloud *reading,
   out->kept = kept;
   out->point_used_ratio = (double)kept / (double)(k * nr);
   out->weighted_point_used_ratio = wsum / (double)(k * nr);
+
+  if (p2plane && force_mode != ORC_FORCE_NONE) {
+    const int nd = force_mode == ORC_FORCE_2D ? 3 : 4;
+    double A[16], b[4];
+    memset(A, 0, sizeof(A));
+    memset(b, 0, sizeof(b));
+    double resid = 0.0;
+    for (int64_t i = 0; i < nr; ++i)
+      for (int kk = 0; kk < k; ++kk) {
+        size_t m = (size_t)i * k + kk;
+        if (isinf(d2[m]) || w[m] == 0.f) continue;
+        const float *pf = reading->feat + 4 * i;
+        const float *qf = reference->feat + 4 * (int64_t)ids[m];
+        const float *nf = reference->normals + 3 * (int64_t)ids[m];
+        double p[3] = {pf[0], pf[1], pf[2]}, n[3] = {nf[0], nf[1], nf[2]};
+        double wt = (double)w[m];
+        double F[4];
+        F[0] = p[0] * n[1] - p[1] * n[0];
+        F[1] = n[0]; F[2] = n[1]; F[3] = n[2];
+        double e = (p[0] - (double)qf[0]) * n[0] + (p[1] - (double)qf[1]) * n[1];
+        if (force_mode == ORC_FORCE_4DOF) e += (p[2] - (double)qf[2]) * n[2];
+        for (int c = 0; c < nd; ++c) {
+          double wf = wt * F[c];
+          for (int r = 0; r <= c; ++r) A[c * nd + r] += wf * F[r];
+          b[c] -= wf * e;
+        }
+        resid += wt * (e * e);
+      }
+    for (int c = 0; c < nd; ++c)
+      for (int r = 0; r < c; ++r) A[r * nd + c] = A[c * nd + r];
+    out->residual = resid;
+    double x[4] = {0, 0, 0, 0};
+    solve_n(nd, A, b, x);
+    yaw_to_T(x[0], x[1], x[2], force_mode == ORC_FORCE_4DOF ? x[3] : 0.0, out->T);
+    return ORC_OK;
+  }
 
   if (p2plane) {
     double A[36], b[6];
@@ -1472,7 +1532,7 @@ static int icp_loop(const orc_icp_config *cfg, const orc_cloud *readingIn,
     res->time_knn_s += now_s() - tk;
     st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, step, reference, ids, d2, k, w);
     if (st) break;
-    st = orc_minimize(cfg->minimizer, cfg->sensor_std_dev, step, reference, ids, d2, w, k, &mo);
+    st = orc_minimize_ex(cfg->minimizer, cfg->force_mode, cfg->sensor_std_dev, step, reference, ids, d2, w, k, &mo);
     if (st) break;
     m4_mul(mo.T, T_iter, T_iter);
     ++iters;
@@ -1608,7 +1668,7 @@ int orc_probe_residual(const orc_icp_config *cfg, const orc_cloud *readingIn,
     st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, rd, reference, ids, d2, k, w);
     if (!st) {
       orc_min_out mo;
-      st = orc_minimize(cfg->minimizer, cfg->sensor_std_dev, rd, reference, ids, d2, w, k, &mo);
+      st = orc_minimize_ex(cfg->minimizer, cfg->force_mode, cfg->sensor_std_dev, rd, reference, ids, d2, w, k, &mo);
       if (!st) *residual = mo.residual;
     }
     orc_kdtree_free(t);

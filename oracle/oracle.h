@@ -136,6 +136,11 @@ typedef struct {
 int orc_minimize(int type, double sensor_std_dev, const orc_cloud *reading,
                  const orc_cloud *reference, const int32_t *ids,
                  const float *d2, const float *w, int k, orc_min_out *out);
+/* PointToPlaneErrorMinimizer{force2D, force4DOF}                            */
+enum { ORC_FORCE_NONE = 0, ORC_FORCE_2D = 1, ORC_FORCE_4DOF = 2 };
+int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_cloud *reading,
+                    const orc_cloud *reference, const int32_t *ids, const float *d2,
+                    const float *w, int k, orc_min_out *out);
 /* getOverlap() on the last error elements (A.5).                           */
 double orc_overlap(int type, const orc_cloud *reading, const orc_cloud *reference,
                    const int32_t *ids, const float *d2, const float *w, int k);
@@ -157,6 +162,7 @@ typedef struct {
   int max_iterations;                             /* Counter; <=0: absent   */
   int has_differential; double min_diff_rot, min_diff_trans; int smooth_length;
   int has_bound; double max_rot_norm, max_trans_norm;
+  int force_mode;                                 /* ORC_FORCE_*            */
 } orc_icp_config;
 void orc_icp_config_default(orc_icp_config *cfg);
 

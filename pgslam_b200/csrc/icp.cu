@@ -50,7 +50,10 @@ constexpr int kAccMaxBlocks = 128;
 // per-pair accumulation of one weighted match (A.5 / A.7), all in fp64
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void accumulate_match(double* acc, int minimizer, const float3 pf, const float4 qf,
-                                                 const float3 nf, double w) {
+                                                 float3 nf, double w, int force_mode = FORCE_NONE) {
+  // force2D: features and normals are cut to x,y (PointToPlane.cpp compute_in_place); with
+  // n.z = 0 the (p x n).z, n.x, n.y rows and the residual are exactly the 2-D ones
+  if (force_mode == FORCE_2D) nf.z = 0.f;
   const double p[3] = {(double)pf.x, (double)pf.y, (double)pf.z};
   if (minimizer == MIN_P2POINT) {
     const double q[3] = {(double)qf.x, (double)qf.y, (double)qf.z};
@@ -204,15 +207,35 @@ __device__ void finish_iteration(PairState& st, const IcpParams& P, const double
     }
   } else {
     double A[36], b[6], x[6];
-    for (int c = 0; c < 6; ++c) {
-      for (int r = 0; r <= c; ++r) {
-        A[c * 6 + r] = acc[tri(c, r)];
-        A[r * 6 + c] = acc[tri(c, r)];
+    if (P.force_mode == FORCE_NONE) {
+      for (int c = 0; c < 6; ++c) {
+        for (int r = 0; r <= c; ++r) {
+          A[c * 6 + r] = acc[tri(c, r)];
+          A[r * 6 + c] = acc[tri(c, r)];
+        }
+        b[c] = acc[21 + c];
       }
-      b[c] = acc[21 + c];
+      solve6(A, b, x);
+      angle_axis_to_T(x, Tinc);
+    } else {
+      // unknowns [yaw, tx, ty(, tz)] = rows/columns 2,3,4(,5) of the 6-DOF system
+      const int nd = P.force_mode == FORCE_2D ? 3 : 4;
+      for (int c = 0; c < nd; ++c) {
+        for (int r = 0; r <= c; ++r) {
+          A[c * nd + r] = acc[tri(c + 2, r + 2)];
+          A[r * nd + c] = acc[tri(c + 2, r + 2)];
+        }
+        b[c] = acc[21 + c + 2];
+      }
+      x[3] = 0.0;
+      if (nd == 3) solve_sym<3>(A, b, x);
+      else solve_sym<4>(A, b, x);
+      m4_identity(Tinc);
+      const double cs = cos(x[0]), sn = sin(x[0]);
+      Tinc[0] = cs; Tinc[4] = -sn;
+      Tinc[1] = sn; Tinc[5] = cs;
+      Tinc[12] = x[1]; Tinc[13] = x[2]; Tinc[14] = nd == 4 ? x[3] : 0.0;
     }
-    solve6(A, b, x);
-    angle_axis_to_T(x, Tinc);
   }
   for (int i = 0; i < 16; ++i) { st.T_prev[i] = st.T_iter[i]; st.T_inc[i] = Tinc[i]; }
   st.xf_prev = st.xf;
@@ -416,6 +439,48 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   v.match_d2[i] = acc.d;
 }
 
+// KDTreeMatcher knn > 1: every reading point keeps its K nearest (ascending, ties -> lower
+// original index); matches are stored [point][neighbour] as sorted positions.  The climb is
+// seeded from the leaf of the previous nearest match.
+template <int K>
+__global__ void __launch_bounds__(128)
+match_k_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2, int k) {
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_r) return;
+  const Xf T = st.xf;
+  float4 r = v.reading[i];
+  float3 q = xform_rn(T, r.x, r.y, r.z);
+  BestK<K> acc;
+  acc.init();
+  const int pp = st.iterations > 0 ? v.match_pos[(size_t)i * k] : -1;
+  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, maxr2, acc);
+  else knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
+  int* op = v.match_pos + (size_t)i * k;
+  float* od = v.match_d2 + (size_t)i * k;
+#pragma unroll
+  for (int e = 0; e < K; ++e) {
+    if (e < k) {
+      const int id = key_id(acc.key[e]);
+      const bool found = id != 0x7fffffff;
+      op[e] = found ? v.ref_inv[id] : -1;
+      od[e] = found ? key_dist(acc.key[e]) : kInfF;
+    }
+  }
+}
+
+__global__ void deactivate_kernel(PairState* st, int status) {
+  st->active = 0;
+  st->status = status;
+}
+
+__global__ void inverse_positions_kernel(const float4* __restrict__ sorted_pts, int n, int* __restrict__ inv) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) inv[__float_as_int(sorted_pts[j].w)] = j;
+}
+
 // Exact quantile of the valid match distances (Matches::getDistsQuantile, A.3)
 // as a 3-pass MSB radix select over the fp32 bit patterns (11 + 11 + 10 bits;
 // non-negative floats order like unsigned ints).  Each pass is one multi-block
@@ -442,11 +507,11 @@ select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ s
   const unsigned mask = pass == 0 ? 0u : st.sel_mask;
   for (int d = tid; d < kSelBins; d += 256) hist[d] = 0;
   __syncthreads();
-  for (int base = blockIdx.x * 256; base < v.n_r; base += gridDim.x * 256) {
+  for (int base = blockIdx.x * 256; base < v.n_m; base += gridDim.x * 256) {
     const int i = base + tid;
     unsigned u = 0;
     bool valid = false;
-    if (i < v.n_r) {
+    if (i < v.n_m) {
       u = __float_as_uint(v.match_d2[i]);
       // getDistsQuantile: dist != inf and dist > 0
       valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
@@ -521,6 +586,18 @@ select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ s
   }
 }
 
+void launch_match_k(int k, dim3 grid, cudaStream_t s, const PairView* views, PairState* states, float maxr2) {
+  if (k == 2) match_k_kernel<2><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k == 3) match_k_kernel<3><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k == 4) match_k_kernel<4><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k <= 6) match_k_kernel<6><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k <= 8) match_k_kernel<8><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k <= 12) match_k_kernel<12><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k <= 16) match_k_kernel<16><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else if (k <= 24) match_k_kernel<24><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+  else match_k_kernel<32><<<grid, 128, 0, s>>>(views, states, maxr2, k);
+}
+
 // no quantile-based filter in the chain: the limits are the fixed ones
 __global__ void fixed_limits_kernel(PairState* __restrict__ states, IcpParams P, int n_pairs) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,16 +615,17 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
   PairState& st = states[blockIdx.y];
   if (!st.active) return;
   const PairView v = views[blockIdx.y];
-  const unsigned slices = (unsigned)reduce_slices(v.n_r, kAccPerBlock, kAccMaxBlocks);
+  const unsigned slices = (unsigned)reduce_slices(v.n_m, kAccPerBlock, kAccMaxBlocks);
   if (blockIdx.x >= slices) return;
   const Xf T = st.xf;
   const float lo = st.lim_lo, hi = st.lim_hi;
   double acc[kAcc];
 #pragma unroll
   for (int j = 0; j < kAcc; ++j) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += slices * blockDim.x) {
-    const int pos = v.match_pos[i];
-    const float d = v.match_d2[i];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < v.n_m; m += slices * blockDim.x) {
+    const int i = P.knn == 1 ? m : m / P.knn;
+    const int pos = v.match_pos[m];
+    const float d = v.match_d2[m];
     // ErrorElements skips dist == inf; OutlierFilters weights are 0/1 here
     bool use = pos >= 0 && d < kInfF;
     if (P.has_outliers) use = use && d <= hi && d >= lo;
@@ -566,7 +644,7 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
       float4 n4 = v.ref_normals[pos];
       n = make_float3(n4.x, n4.y, n4.z);
     }
-    accumulate_match(acc, P.minimizer, p, q, n, 1.0);
+    accumulate_match(acc, P.minimizer, p, q, n, 1.0, P.force_mode);
   }
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -608,7 +686,7 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
   PairState& st = states[blockIdx.y];
   if (st.status != PGS_OK || st.iterations == 0) return;
   const PairView v = views[blockIdx.y];
-  const unsigned slices = (unsigned)reduce_slices(v.n_r, kAccPerBlock, kAccMaxBlocks);
+  const unsigned slices = (unsigned)reduce_slices(v.n_m, kAccPerBlock, kAccMaxBlocks);
   if (blockIdx.x >= slices) return;
   const Xf T = st.xf_prev;
   const float lo = st.lim_lo, hi = st.lim_hi;
@@ -626,9 +704,10 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
   double acc[kAcc2];
 #pragma unroll
   for (int j = 0; j < kAcc2; ++j) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n_r; i += slices * blockDim.x) {
-    const int pos = v.match_pos[i];
-    const float d = v.match_d2[i];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < v.n_m; m += slices * blockDim.x) {
+    const int i = P.knn == 1 ? m : m / P.knn;
+    const int pos = v.match_pos[m];
+    const float d = v.match_d2[m];
     bool use = pos >= 0 && d < kInfF;
     if (P.has_outliers) use = use && d <= hi && d >= lo;
     if (!use) continue;
@@ -692,7 +771,7 @@ __global__ void finish_kernel(const PairView* __restrict__ views, PairState* __r
   m4_mul(st.T_iter, st.T_refMean_dataIn, tmp);
   m4_mul(st.T_refIn_refMean, tmp, st.T_out);
   if (st.status != PGS_OK || st.iterations == 0) return;
-  const double denom = (double)v.n_r;  // k == 1
+  const double denom = (double)v.n_m;  // knn * N_r
   const bool want_overlap = v.rd_normals != nullptr && v.rd_noise != nullptr && P.minimizer != MIN_P2POINT;
   st.overlap = want_overlap ? (st.acc2[43] > 0.0 ? st.acc2[42] / st.acc2[43] : 0.0) : st.wsum / denom;
   if (P.minimizer == MIN_P2PLANE_COV) {
@@ -746,7 +825,7 @@ struct ExplicitJob {
 
 __global__ void __launch_bounds__(256)
 explicit_accumulate_kernel(ExplicitJob job, int minimizer, int pass, double alpha, double beta, double gamma,
-                           double t0, double t1, double t2) {
+                           double t0, double t1, double t2, int force_mode) {
   __shared__ double sh[8][kAcc2];
   double acc[kAcc2];
 #pragma unroll
@@ -765,7 +844,7 @@ explicit_accumulate_kernel(ExplicitJob job, int minimizer, int pass, double alph
     float3 n = make_float3(0.f, 0.f, 0.f);
     if (job.ref_normals) n = make_float3(job.ref_normals[3 * id], job.ref_normals[3 * id + 1], job.ref_normals[3 * id + 2]);
     if (pass == 0) {
-      accumulate_match(acc, minimizer, p, q, n, (double)w);
+      accumulate_match(acc, minimizer, p, q, n, (double)w, force_mode);
     } else {
       if (minimizer == MIN_P2PLANE_COV) accumulate_cov(acc, p, q, n, alpha, beta, gamma, t);
       if (job.rd_normals && job.rd_noise && minimizer != MIN_P2POINT) {
@@ -930,6 +1009,18 @@ void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p) {
   }
 }
 
+// PointToPlaneErrorMinimizer{force2D, force4DOF}; force2D wins when both are set, as in
+// upstream's compute_in_place (the 2-D branch is taken first)
+int force_mode_of(const Module& minimizer) {
+  if (minimizer.name == "PointToPointErrorMinimizer") return FORCE_NONE;
+  const bool f2 = minimizer.flag("force2D"), f4 = minimizer.flag("force4DOF");
+  if (!f2 && !f4) return FORCE_NONE;
+  if (minimizer.name == "PointToPlaneWithCovErrorMinimizer")
+    throw Error(PGS_INVALID_PARAMETER, "PointToPlaneWithCovErrorMinimizer: the covariance estimate is 6-DOF; "
+                                       "force2D / force4DOF are not supported with it");
+  return f2 ? FORCE_2D : FORCE_4DOF;
+}
+
 IcpParams params_from_chain(const ChainConfig& cfg) {
   IcpParams p;
   std::memset(&p, 0, sizeof(p));
@@ -938,8 +1029,7 @@ IcpParams params_from_chain(const ChainConfig& cfg) {
   else if (mn == "PointToPlaneWithCovErrorMinimizer") p.minimizer = MIN_P2PLANE_COV;
   else if (mn == "PointToPointErrorMinimizer") p.minimizer = MIN_P2POINT;
   else throw Error(PGS_INVALID_ELEMENT, "ErrorMinimizer " + mn + " has no device implementation");
-  if (p.minimizer != MIN_P2POINT && (cfg.minimizer.flag("force2D") || cfg.minimizer.flag("force4DOF")))
-    throw Error(PGS_INVALID_PARAMETER, mn + ": force2D / force4DOF are not supported");
+  p.force_mode = force_mode_of(cfg.minimizer);
   p.sensor_std_dev = p.minimizer == MIN_P2PLANE_COV ? cfg.minimizer.real("sensorStdDev") : 0.01;
   p.max_iterations = 0;
   p.has_diff = 0;
@@ -963,12 +1053,10 @@ IcpParams params_from_chain(const ChainConfig& cfg) {
   p.hard_iteration_cap = p.max_iterations > 0 ? p.max_iterations : 1000;
   outlier_limits_params(cfg.outlier_filters, &p);
   if (cfg.matcher.name != "KDTreeMatcher") throw Error(PGS_INVALID_ELEMENT, "Matcher " + cfg.matcher.name + " has no device implementation");
-  if (cfg.matcher.integer("knn") != 1)
-    throw Error(PGS_INVALID_PARAMETER, "the fused ICP loop supports KDTreeMatcher knn = 1 (use the Matcher module for knn > 1)");
+  p.knn = (int)cfg.matcher.integer("knn");
+  if (p.knn < 1 || p.knn > 32) throw Error(PGS_INVALID_PARAMETER, "KDTreeMatcher: knn must be in [1, 32]");
   float md = (float)cfg.matcher.real("maxDist");
   p.max_r2 = std::isinf(md) ? kInfF : md * md;
-  if (!cfg.reading_step_filters.empty())
-    throw Error(PGS_INVALID_PARAMETER, "readingStepDataPointsFilters are not supported by the fused ICP loop");
   return p;
 }
 
@@ -1049,6 +1137,11 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
       pr->normals_sorted.reset(ctx, (size_t)ns[b]);
       gather_vec3_sorted_kernel<<<ceil_div(ns[b], 256), 256, 0, s>>>(pr->index->pts.p, ns[b], nrm->data.p, 3,
                                                                     pr->normals_sorted.p, nullptr);
+      ctx_count_launches(ctx, 1);
+    }
+    if (params_.knn > 1 && ns[b] > 0) {
+      pr->inv_pos.reset(ctx, (size_t)ns[b]);
+      inverse_positions_kernel<<<ceil_div(ns[b], 256), 256, 0, s>>>(pr->index->pts.p, ns[b], pr->inv_pos.p);
       ctx_count_launches(ctx, 1);
     }
     pr->cloud = std::move(refs[b]);
@@ -1158,6 +1251,24 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       ctx_count_launches(ctx, 1);
     }
   }
+  // readingStepDataPointsFilters (§3.3): upstream re-applies them every iteration to a fresh
+  // copy of the reading as it stands here (filtered, moved by T_refMean_dataIn), before the
+  // step transform.  Every filter of this library is a deterministic function of its input,
+  // so each iteration would produce this same cloud: apply once.
+  if (!cfg_.reading_step_filters.empty()) {
+    apply_filters(ctx, cfg_.reading_step_filters, rdp);
+    max_nr = 0;
+    for (int p = 0; p < P; ++p) {
+      max_nr = std::max(max_nr, (int)rdp[p]->n);
+      if (rdp[p]->n == 0 && hs[p].active) {  // nothing left to match: "no outlier to filter"
+        hs[p].active = 0;
+        hs[p].status = PGS_CONVERGENCE_ERROR;
+        --n_active;
+        deactivate_kernel<<<1, 1, 0, s>>>(d_states.p + p, PGS_CONVERGENCE_ERROR);
+        ctx_count_launches(ctx, 1);
+      }
+    }
+  }
   std::vector<std::unique_ptr<Index>> rd_sorted;
   {
     std::vector<const float4*> pts(P);
@@ -1167,7 +1278,10 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   }
 
   // ---- per-pair views ----------------------------------------------------------
-  const int acc_blocks = reduce_slices(max_nr, kAccPerBlock, kAccMaxBlocks);
+  const int knn = prm.knn;
+  if ((int64_t)max_nr * knn > 0x7fffffff) throw Error(PGS_INVALID_PARAMETER, "knn x reading points exceeds 2^31");
+  const int max_nm = max_nr * knn;
+  const int acc_blocks = reduce_slices(max_nm, kAccPerBlock, kAccMaxBlocks);
   std::vector<PairView> hv(P);
   std::vector<DBuf<int>> mpos(P);
   std::vector<DBuf<float>> md2(P);
@@ -1178,13 +1292,15 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   std::vector<DBuf<float>> rdnoise(P);
   for (int p = 0; p < P; ++p) {
     const int nr = (int)rdp[p]->n;
-    mpos[p].reset(ctx, (size_t)std::max(nr, 1));
-    md2[p].reset(ctx, (size_t)std::max(nr, 1));
+    mpos[p].reset(ctx, (size_t)std::max(nr, 1) * knn);
+    md2[p].reset(ctx, (size_t)std::max(nr, 1) * knn);
     partials[p].reset(ctx, (size_t)acc_blocks * kAcc2);
     PairView v;
     std::memset(&v, 0, sizeof(v));
     v.reading = rd_sorted[p]->pts.p;
     v.n_r = nr;
+    v.n_m = nr * knn;
+    v.ref_inv = refs[p]->inv_pos.p;
     v.tree = refs[p]->index->view();
     v.ref_normals = refs[p]->has_normals ? refs[p]->normals_sorted.p : nullptr;
     const Desc* nrm = rdp[p]->find("normals");
@@ -1221,7 +1337,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   std::vector<cudaEvent_t> kev;  // profiling only: 4 marks per iteration
   const int max_it = prm.hard_iteration_cap;
   const dim3 gm(ceil_div(std::max(max_nr, 1), 128), P), ga(acc_blocks, P);
-  const dim3 gs(std::max(1, std::min(kSelBlocks, ceil_div(max_nr, 2048))), P);
+  const dim3 gs(std::max(1, std::min(kSelBlocks, ceil_div(max_nm, 2048))), P);
   if (prm.n_quant == 0) {
     fixed_limits_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, P);
     ctx_count_launches(ctx, 1);
@@ -1241,7 +1357,8 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       kev.push_back(e);
     };
     mark();
-    match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+    if (knn == 1) match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+    else launch_match_k(knn, gm, s, d_views.p, d_states.p, prm.max_r2);
     mark();
     for (int jq = 0; jq < prm.n_quant; ++jq)
       for (int pass = 0; pass < 3; ++pass)
@@ -1281,8 +1398,8 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     r.n_reference = refs[p]->index->n;
     if (st.status == PGS_OK && st.iterations > 0 && rdp[p]->n > 0) {
       r.overlap = st.overlap;
-      r.weighted_point_used_ratio = st.wsum / (double)rdp[p]->n;
-      r.point_used_ratio = st.kept / (double)rdp[p]->n;
+      r.weighted_point_used_ratio = st.wsum / ((double)rdp[p]->n * knn);
+      r.point_used_ratio = st.kept / ((double)rdp[p]->n * knn);
       r.residual = st.resid;
     }
   }
@@ -1400,7 +1517,8 @@ void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, co
       acc[j] = s;
     }
   };
-  explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 0, 0, 0, 0, 0, 0, 0);
+  const int force_mode = force_mode_of(minimizer);
+  explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 0, 0, 0, 0, 0, 0, 0, force_mode);
   ctx_count_launches(ctx, 1);
   PGS_LAUNCH_CHECK();
   double acc[kAcc2];
@@ -1427,6 +1545,8 @@ void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, co
   IcpParams prm;
   std::memset(&prm, 0, sizeof(prm));
   prm.minimizer = mz;
+  prm.force_mode = force_mode;
+  prm.knn = 1;
   prm.hard_iteration_cap = 1 << 30;
   prm.sensor_std_dev = mz == MIN_P2PLANE_COV ? minimizer.real("sensorStdDev") : 0.01;
   ctx->ensure_progress();
@@ -1446,7 +1566,7 @@ void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, co
     double alpha = std::atan2(Ti[6], Ti[10]);
     double cb = std::cos(beta);
     double gamma = std::atan2(Ti[1] / cb, Ti[0] / cb);
-    explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 1, alpha, beta, gamma, Ti[12], Ti[13], Ti[14]);
+    explicit_accumulate_kernel<<<nb, 256, 0, ctx->stream>>>(job, mz, 1, alpha, beta, gamma, Ti[12], Ti[13], Ti[14], force_mode);
     ctx_count_launches(ctx, 1);
     PGS_LAUNCH_CHECK();
     double acc2[kAcc2];
@@ -1461,6 +1581,7 @@ void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, co
       PairView v;
       std::memset(&v, 0, sizeof(v));
       v.n_r = (int)reading.n;
+      v.n_m = (int)total;
       DBuf<PairView> dv(ctx, 1);
       ctx->upload_small(dv.p, &v, sizeof(v));
       finish_kernel<<<1, 32, 0, ctx->stream>>>(dv.p, st.p, prm, 1);

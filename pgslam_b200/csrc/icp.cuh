@@ -38,7 +38,11 @@ struct IcpParams {
   int hard_iteration_cap;
   int has_sn;          // SurfaceNormalOutlierFilter present
   float sn_eps;        // cos(maxAngle)
+  int knn;             // KDTreeMatcher knn: every reading point is paired with its k nearest
+  int force_mode;      // PointToPlane: 0 = 6-DOF, 1 = force2D (theta,x,y), 2 = force4DOF (yaw,x,y,z)
 };
+
+enum { FORCE_NONE = 0, FORCE_2D = 1, FORCE_4DOF = 2 };
 
 struct PairState {
   double T_init[16];
@@ -66,6 +70,8 @@ struct PairState {
 struct PairView {
   const float4* reading;  // pre-transformed reading, Morton order (w = original index)
   int n_r;
+  int n_m;                     // matches = knn * n_r, stored [point][neighbour] like PM's k x N Matches
+  const int* ref_inv;          // original reference index -> sorted position (knn > 1 only)
   TreeView tree;               // reference index
   const float4* ref_normals;   // per sorted reference position, or null
   const float4* rd_normals;    // per sorted reading position (pre-transformed), or null
@@ -81,6 +87,7 @@ struct PreparedRef {
   std::unique_ptr<Cloud> cloud;   // filtered reference (original order, NOT centred unless setMap)
   std::unique_ptr<Index> index;   // centred, sorted
   DBuf<float4> normals_sorted;
+  DBuf<int> inv_pos;              // original index -> sorted position, built on first use (knn > 1)
   bool has_normals = false;
   double T_refIn_refMean[16];
 };

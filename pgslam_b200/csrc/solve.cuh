@@ -71,58 +71,60 @@ __device__ void jacobi_sym(double* A, double* w, double* V) {
   for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
 }
 
-// A x = b for symmetric PSD 6x6: Cholesky, else minimum-norm via eigen-decomposition
-__device__ inline int solve6(const double* A, const double* b, double* x) {
-  double L[36];
+// A x = b for symmetric PSD N x N: Cholesky, else minimum-norm via eigen-decomposition
+template <int N>
+__device__ inline int solve_sym(const double* A, const double* b, double* x) {
+  double L[N * N];
   double maxd = 0.0;
-  for (int i = 0; i < 6; ++i)
-    if (A[i * 6 + i] > maxd) maxd = A[i * 6 + i];
+  for (int i = 0; i < N; ++i)
+    if (A[i * N + i] > maxd) maxd = A[i * N + i];
   bool ok = maxd > 0.0;
-  for (int i = 0; i < 36; ++i) L[i] = 0.0;
-  for (int j = 0; j < 6 && ok; ++j) {
-    double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= L[k * 6 + j] * L[k * 6 + j];
+  for (int i = 0; i < N * N; ++i) L[i] = 0.0;
+  for (int j = 0; j < N && ok; ++j) {
+    double d = A[j * N + j];
+    for (int k = 0; k < j; ++k) d -= L[k * N + j] * L[k * N + j];
     if (!(d > 1e-12 * maxd)) { ok = false; break; }
     double ljj = sqrt(d);
-    L[j * 6 + j] = ljj;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[j * 6 + i];
-      for (int k = 0; k < j; ++k) s -= L[k * 6 + i] * L[k * 6 + j];
-      L[j * 6 + i] = s / ljj;
+    L[j * N + j] = ljj;
+    for (int i = j + 1; i < N; ++i) {
+      double s = A[j * N + i];
+      for (int k = 0; k < j; ++k) s -= L[k * N + i] * L[k * N + j];
+      L[j * N + i] = s / ljj;
     }
   }
   if (ok) {
-    double y[6];
-    for (int i = 0; i < 6; ++i) {
+    double y[N];
+    for (int i = 0; i < N; ++i) {
       double s = b[i];
-      for (int k = 0; k < i; ++k) s -= L[k * 6 + i] * y[k];
-      y[i] = s / L[i * 6 + i];
+      for (int k = 0; k < i; ++k) s -= L[k * N + i] * y[k];
+      y[i] = s / L[i * N + i];
     }
-    for (int i = 5; i >= 0; --i) {
+    for (int i = N - 1; i >= 0; --i) {
       double s = y[i];
-      for (int k = i + 1; k < 6; ++k) s -= L[i * 6 + k] * x[k];
-      x[i] = s / L[i * 6 + i];
+      for (int k = i + 1; k < N; ++k) s -= L[i * N + k] * x[k];
+      x[i] = s / L[i * N + i];
     }
-    return 6;
+    return N;
   }
-  double B[36], w[6], V[36];
-  for (int i = 0; i < 36; ++i) B[i] = A[i];
-  jacobi_sym<6>(B, w, V);
+  double B[N * N], w[N], V[N * N];
+  for (int i = 0; i < N * N; ++i) B[i] = A[i];
+  jacobi_sym<N>(B, w, V);
   double wmax = 0.0;
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < N; ++i)
     if (fabs(w[i]) > wmax) wmax = fabs(w[i]);
-  for (int i = 0; i < 6; ++i) x[i] = 0.0;
+  for (int i = 0; i < N; ++i) x[i] = 0.0;
   int rank = 0;
-  for (int e = 0; e < 6; ++e) {
+  for (int e = 0; e < N; ++e) {
     if (!(w[e] > 1e-12 * wmax)) continue;
     ++rank;
     double vb = 0.0;
-    for (int i = 0; i < 6; ++i) vb += V[e * 6 + i] * b[i];
+    for (int i = 0; i < N; ++i) vb += V[e * N + i] * b[i];
     vb = vb / w[e];
-    for (int i = 0; i < 6; ++i) x[i] += vb * V[e * 6 + i];
+    for (int i = 0; i < N; ++i) x[i] += vb * V[e * N + i];
   }
   return rank;
 }
+__device__ inline int solve6(const double* A, const double* b, double* x) { return solve_sym<6>(A, b, x); }
 
 __device__ inline void inv6_sym(const double* H, double* Hi) {
   for (int c = 0; c < 6; ++c) {

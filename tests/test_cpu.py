@@ -94,6 +94,10 @@ logger: NullLogger
 """
     assert pm.check_config(block) == 9
     assert pm.check_config("readingStepDataPointsFilters: []\nmatcher: KDTreeMatcher\n") == 4
+    # chains the fused loop accepts since round 1b: knn > 1, step filters, force2D / force4DOF
+    assert pm.check_config("readingStepDataPointsFilters:\n  - MaxDistDataPointsFilter: {maxDist: 30}\n"
+                           "matcher:\n  KDTreeMatcher: {knn: 3}\n"
+                           "errorMinimizer:\n  PointToPlaneErrorMinimizer: {force4DOF: 1}\n") == 5
 
 
 @pytest.mark.parametrize("text,exc", [
@@ -103,8 +107,8 @@ logger: NullLogger
     ("outlierFilters:\n  - TrimmedDistOutlierFilter: {ratio: 2}\n", pm.InvalidParameter),
     ("matcher: NoSuchMatcher\n", pm.InvalidElement),
     ("somethingElse:\n  - X\n", pm.InvalidModuleType),
-    ("matcher:\n  KDTreeMatcher: {knn: 3}\n", pm.InvalidParameter),  # fused loop is k = 1
-    ("errorMinimizer:\n  PointToPlaneErrorMinimizer: {force2D: 1}\n", pm.InvalidParameter),
+    ("matcher:\n  KDTreeMatcher: {knn: 33}\n", pm.InvalidParameter),  # register k-lists: knn <= 32
+    ("errorMinimizer:\n  PointToPlaneWithCovErrorMinimizer: {force2D: 1}\n", pm.InvalidParameter),
 ])
 def test_config_check_rejects_like_libpointmatcher(text, exc):
     with pytest.raises(exc):
@@ -254,6 +258,87 @@ def test_oracle_icp_recovers_a_known_rigid_motion(minimizer):
     r = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf))
     assert r["status"] == 0 and not r["max_iter_reached"]
     np.testing.assert_allclose(r["T"], T, atol=1e-5)
+
+
+def _box_room(n, seed):
+    g = np.random.default_rng(seed)
+    faces = []
+    for axis, val in ((0, -5.0), (0, 5.0), (1, -4.0), (1, 4.0), (2, 0.0), (2, 3.0)):
+        p = np.stack([g.uniform(-5, 5, n), g.uniform(-4, 4, n), g.uniform(0, 3, n)])
+        p[axis] = val
+        faces.append(p)
+    rf = np.ones((4, 6 * n), np.float32)
+    rf[:3] = np.concatenate(faces, axis=1).astype(np.float32)
+    return rf
+
+
+@pytest.mark.parametrize("mode,T", [
+    ("force4DOF", synth.pose_matrix([0.12, -0.08, 0.05], 0.04, 0.0, 0.0)),  # yaw + xyz
+    ("force2D", synth.pose_matrix([0.12, -0.08, 0.0], 0.04, 0.0, 0.0)),     # yaw + xy
+])
+def test_oracle_forced_minimizers_recover_a_motion_inside_their_subspace(mode, T):
+    """PointToPlaneErrorMinimizer{force2D, force4DOF}: a motion that lies in the restricted
+    parameter space is recovered; the 6-DOF solve of the same case agrees with it."""
+    rf = _box_room(3000, 4)
+    rd = (np.linalg.inv(T) @ rf.astype(np.float64)).astype(np.float32)
+    chk = [{"CounterTransformationChecker": {"maxIterationCount": 400}},
+           {"DifferentialTransformationChecker": {"minDiffRotErr": 1e-7, "minDiffTransErr": 1e-7}}]
+    cfg = dict(util.C2, errorMinimizer={"PointToPlaneErrorMinimizer": {mode: 1}},
+               outlierFilters=[{"TrimmedDistOutlierFilter": {"ratio": 0.95}}], transformationCheckers=chk)
+    r = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf))
+    assert r["status"] == 0 and not r["max_iter_reached"]
+    np.testing.assert_allclose(r["T"], T, atol=2e-5)
+    # the estimate never leaves the subspace: rotation about z only (and no z shift in 2-D)
+    np.testing.assert_allclose(r["T"][2, :3], [0, 0, 1], atol=1e-12)
+    np.testing.assert_allclose(r["T"][:3, 2], [0, 0, 1], atol=1e-12)
+    if mode == "force2D":
+        assert abs(r["T"][2, 3]) < 1e-6
+
+
+def test_oracle_forced_minimizer_is_the_restricted_least_squares_solution():
+    """One compute() against numpy: the forced solve equals lstsq over the kept columns of F."""
+    rd, rf, _ = synth.scan_pair(21, beams=16, az_steps=200)
+    oref = ob.Cloud(rf)
+    ob.apply_filter(oref, "SurfaceNormalDataPointsFilter", knn=10)
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    w = np.ones_like(d2)
+    P = rd[:3].astype(np.float64).T
+    Q = rf[:3, ids[0]].astype(np.float64).T
+    N = oref.desc("normals")[:, ids[0]].astype(np.float64).T
+    for mode, cols in ((1, [2, 3, 4]), (2, [2, 3, 4, 5])):
+        st, got = ob.minimize(ob.E_POINT_TO_PLANE, ob.Cloud(rd), oref, ids, d2, w, force_mode=mode)
+        assert st == 0
+        Nn = N.copy()
+        if mode == 1:
+            Nn[:, 2] = 0.0
+        F = np.concatenate([np.cross(P, Nn), Nn], axis=1)[:, cols]
+        e = ((P - Q) * Nn).sum(axis=1)
+        x = np.linalg.solve(F.T @ F, -F.T @ e)
+        c, s_ = np.cos(x[0]), np.sin(x[0])
+        want = np.eye(4)
+        want[:2, :2] = [[c, -s_], [s_, c]]
+        want[:len(cols) - 1, 3] = x[1:]
+        np.testing.assert_allclose(got["T"], want, rtol=0, atol=1e-10)
+        assert got["residual"] == pytest.approx(float((e * e).sum()), rel=1e-10)
+
+
+def test_oracle_icp_with_knn_3_and_step_filters():
+    """knn > 1 pairs every reading point with its 3 nearest (ratios over k*N); a step filter is
+    applied to the reading on every iteration before the step transform."""
+    rd, rf, truth = synth.scan_pair(22, beams=16, az_steps=400)
+    base = ob.icp_run(util.C2, ob.Cloud(rd), ob.Cloud(rf))
+    k3 = ob.icp_run(dict(util.C2, matcher={"KDTreeMatcher": {"knn": 3}}), ob.Cloud(rd), ob.Cloud(rf))
+    assert base["status"] == k3["status"] == 0
+    assert k3["point_used_ratio"] == pytest.approx(0.85, abs=1e-3)
+    assert np.abs(k3["T"][:3, 3] - truth[:3, 3]).max() < 0.05
+    step = dict(util.C2, readingStepDataPointsFilters=[{"MaxDistDataPointsFilter": {"maxDist": 20.0}}])
+    s1 = ob.icp_run(step, ob.Cloud(rd), ob.Cloud(rf))
+    # the same filter as a reading filter acts in the sensor frame instead of the centred map frame
+    pre = dict(util.C2, readingDataPointsFilters=[{"MaxDistDataPointsFilter": {"maxDist": 20.0}}])
+    s2 = ob.icp_run(pre, ob.Cloud(rd), ob.Cloud(rf))
+    assert s1["status"] == s2["status"] == 0
+    assert not np.array_equal(s1["T"], s2["T"])
+    assert np.abs(s1["T"][:3, 3] - truth[:3, 3]).max() < 0.05
 
 
 def test_oracle_icp_is_equivariant_under_a_common_rigid_motion():

@@ -762,3 +762,72 @@ def test_planar_scene_takes_the_rank_deficient_solve(pm):
     assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
     util.assert_pose_close(Tg, want["T"], 1e-7, 1e-7)
     assert abs(Tg[2, 3] - 0.07) < 1e-3  # the constrained DOF is recovered
+
+
+# ------------------------------------------- chains the fused loop gained in round 1b ---
+@pytest.mark.parametrize("k", [2, 3, 7])
+def test_icp_fused_loop_with_knn_greater_than_one(pm, pair30k, k):
+    rd, rf, _ = pair30k
+    cfg = dict(util.C2, matcher={"KDTreeMatcher": {"knn": k, "epsilon": 0}})
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["point_used_ratio"] == pytest.approx(want["point_used_ratio"], rel=1e-12)
+    assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+    assert icp.last["residual"] == pytest.approx(want["residual"], rel=1e-7)
+
+
+def test_icp_knn_with_max_dist_cov_and_point_to_point(pm, pair30k):
+    rd, rf, _ = pair30k
+    for cfg in (dict(util.C2_COV, matcher={"KDTreeMatcher": {"knn": 4, "maxDist": 0.5}}),
+                dict(util.C1, matcher={"KDTreeMatcher": {"knn": 2}})):
+        icp, T, want = _run_both(pm, cfg, rd, rf)
+        assert want["status"] == 0
+        assert icp.last["iterations"] == want["iterations"]
+        util.assert_pose_close(T, want["T"])
+        assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+        if "WithCov" in str(cfg["errorMinimizer"]):
+            np.testing.assert_allclose(icp.errorMinimizer.getCovariance(), want["cov"], rtol=1e-6, atol=1e-16)
+
+
+def test_icp_reading_step_filters(pm, pair30k):
+    rd, rf, _ = pair30k
+    cfg = dict(util.C2, readingStepDataPointsFilters=[
+        {"MaxDistDataPointsFilter": {"maxDist": 20.0}},
+        {"RandomSamplingDataPointsFilter": {"prob": 0.6, "seed": 11}}])
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    assert 0 < icp.last["n_reading"] < rd.shape[1]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+    # a step filter that removes everything: nothing to match -> ConvergenceError on both sides
+    none = dict(util.C2, readingStepDataPointsFilters=[{"MaxDistDataPointsFilter": {"maxDist": 1e-3}}])
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(none))
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    assert ob.icp_run(none, ob.Cloud(rd), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+
+
+@pytest.mark.parametrize("mode", ["force2D", "force4DOF"])
+def test_icp_point_to_plane_forced_modes(pm, pair30k, mode):
+    rd, rf, _ = pair30k
+    cfg = dict(util.C2, errorMinimizer={"PointToPlaneErrorMinimizer": {mode: 1}})
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["residual"] == pytest.approx(want["residual"], rel=1e-7)
+    np.testing.assert_allclose(T[2, :3], [0, 0, 1], atol=1e-12)
+    # module-level compute() of the same minimizer
+    oref = ob.Cloud(rf)
+    ob.apply_filter(oref, "SurfaceNormalDataPointsFilter", knn=10)
+    ids, d2 = ob.kdtree_knn(rf, rd, k=1)
+    st, w = ob.outlier_weights([{"TrimmedDistOutlierFilter": {"ratio": 0.85}}], d2)
+    st, ref_out = ob.minimize(ob.E_POINT_TO_PLANE, ob.Cloud(rd), oref, ids, d2, w, force_mode=1 if mode == "force2D" else 2)
+    e = pm.ErrorMinimizer("PointToPlaneErrorMinimizer", {mode: 1})
+    Tm = e.compute(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": oref.desc("normals")}), w, pm.Matches(ids, d2))
+    np.testing.assert_allclose(Tm, ref_out["T"], rtol=0, atol=1e-11)
+    assert e._last.residual == pytest.approx(ref_out["residual"], rel=1e-11)
