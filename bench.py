@@ -163,9 +163,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=48, help="distinct pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=96, help="distinct pairs per GPU per step")
     ap.add_argument("--cpu-steps", type=int, default=0, help="registrations for the cpu_baseline leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-streams", type=int, default=4,
+                    help="worker streams the library splits a batch over (pgs_ctx_set_batch_streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -204,6 +206,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
     ctx = pm.Context(local_rank, stream.cuda_stream)
+    ctx.set_batch_streams(args.batch_streams)
     icp = pm.ICP(ctx)
     icp.loadFromYaml(util.to_yaml(c2_config()))
 
@@ -278,11 +281,15 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     launches0 = ctx.launch_count
-    ctx.set_profiling(True)
     ms, res = timed(step_resident, args.steps)
-    stage = ctx.stage_times()  # of the last step
-    ctx.set_profiling(False)
     launches = ctx.launch_count - launches0
+    # per-kernel CUDA-event timings of one more identical step, taken with the batch on ONE
+    # stream: with the sub-batches overlapping on several streams an event pair around a kernel
+    # would also time whatever the other streams run in between
+    ctx.set_profiling(True)
+    step_resident()
+    stage = ctx.stage_times()
+    ctx.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
 
     for _ in range(args.warmup):
@@ -329,6 +336,7 @@ def main():
                 "peak_source": peak_src, "launches": stage["iterations_launched"],
                 "avg_launch_ms": stage["match_ms"] / max(stage["iterations_launched"], 1),
                 "algorithmic_bytes_per_step": alg_bytes,
+                "timing": "CUDA events around every launch of one extra step after the timed region, whole batch on one stream",
                 "stage_ms_last_step": {k: round(float(v), 3) for k, v in stage.items()}}
     reg_bytes = 68.0 * n_ref + 32.0 * n_pts + statistics.mean(iters) * ((32 + 32 * 0.85) * n_pts + 16.0 * n_ref)
     roofline["whole_registration"] = {"algorithmic_bytes": reg_bytes, "achieved_gbs": reg_bytes * value / world / 1e9,
@@ -344,6 +352,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 points / f64 reductions", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "points_per_scan": n_pts,
+                       "batch_streams": args.batch_streams,
                        "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
                        "parallelism": f"{world} GPU(s), independent pairs per rank, NCCL all_gather of 4x4 results"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,

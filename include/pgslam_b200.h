@@ -230,6 +230,10 @@ typedef struct {
   int32_t iterations_launched;
 } pgs_stage_times;
 pgs_status pgs_ctx_set_profiling(pgs_ctx *ctx, int enabled);
+/* pgs_icp_run_batch splits a batch of independent pairs over this many worker
+ * streams / host threads of the context (default 4; 1 = everything on the
+ * context's own stream).  Results are bit-identical whatever the split.       */
+pgs_status pgs_ctx_set_batch_streams(pgs_ctx *ctx, int n_streams);
 pgs_status pgs_ctx_last_stage_times(const pgs_ctx *ctx, pgs_stage_times *out);
 
 #ifdef __cplusplus

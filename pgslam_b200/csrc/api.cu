@@ -172,15 +172,7 @@ pgs_status pgs_ctx_create(int device, void* stream, pgs_ctx** out) {
 void pgs_ctx_destroy(pgs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->c.device);
-  cudaStreamSynchronize(ctx->c.stream);
-  if (ctx->c.pinned) cudaFreeHost(ctx->c.pinned);
-  if (ctx->c.h_progress) cudaFreeHost((void*)ctx->c.h_progress);
-  for (auto& e : ctx->c.loop_ev)
-    if (e) cudaEventDestroy(e);
-  for (auto& e : ctx->c.copy_ev)
-    if (e) cudaEventDestroy(e);
-  if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
-  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  ctx->c.destroy_resources();
   delete ctx;
 }
 
@@ -238,6 +230,12 @@ uint64_t pgs_ctx_launch_count(const pgs_ctx* ctx) { return ctx->c.launches; }
 
 pgs_status pgs_ctx_set_profiling(pgs_ctx* ctx, int enabled) {
   ctx->c.profiling = enabled != 0;
+  return PGS_OK;
+}
+
+pgs_status pgs_ctx_set_batch_streams(pgs_ctx* ctx, int n_streams) {
+  if (n_streams < 1 || n_streams > 32) return fail(&ctx->c, PGS_INVALID_ARGUMENT, "batch streams must be in [1, 32]");
+  ctx->c.batch_streams = n_streams;
   return PGS_OK;
 }
 

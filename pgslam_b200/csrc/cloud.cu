@@ -42,6 +42,39 @@ void Ctx::upload_small(void* dst, const void* src, size_t bytes) {
   PGS_CUDA(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, stream));
 }
 
+Ctx* Ctx::worker(int i) {
+  while ((int)workers.size() <= i) {
+    Ctx* w = new Ctx();
+    w->device = device;
+    w->num_sms = num_sms;
+    w->batch_streams = 1;
+    PGS_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    w->own_stream = true;
+    workers.push_back(w);
+  }
+  return workers[i];
+}
+
+void Ctx::destroy_resources() {
+  for (Ctx* w : workers) {
+    w->destroy_resources();
+    delete w;
+  }
+  workers.clear();
+  cudaStreamSynchronize(stream);
+  if (pinned) cudaFreeHost(pinned);
+  if (h_progress) cudaFreeHost((void*)h_progress);
+  for (auto& e : loop_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (fork_ev) cudaEventDestroy(fork_ev);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (own_stream) cudaStreamDestroy(stream);
+  pinned = nullptr;
+  h_progress = nullptr;
+}
+
 void Ctx::ensure_progress() {
   if (h_progress) return;
   void* h = nullptr;
@@ -75,7 +108,8 @@ void Cloud::remove(const std::string& label) {
     }
 }
 
-std::unique_ptr<Cloud> Cloud::clone() const {
+std::unique_ptr<Cloud> Cloud::clone(Ctx* target) const {
+  Ctx* ctx = target ? target : this->ctx;
   auto c = std::make_unique<Cloud>(ctx);
   c->n = n;
   c->kd_order = kd_order;  // same points, same order, same index

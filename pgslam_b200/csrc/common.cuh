@@ -63,6 +63,15 @@ struct Ctx {
   cudaStream_t copy_stream = nullptr;  // uploads from pinned host memory overlap with compute
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   void ensure_progress();
+  // A large batch of independent pairs is split over `batch_streams` worker contexts, each
+  // with its own stream and host thread, so that one sub-batch's latency-bound tails (the
+  // small select / solve kernels, host bookkeeping between launches) overlap the others'
+  // wide kernels.  Results do not depend on the split (per-pair reduction order).
+  int batch_streams = 4;
+  std::vector<Ctx*> workers;  // owned; created on first use
+  cudaEvent_t fork_ev = nullptr;
+  Ctx* worker(int i);
+  void destroy_resources();
 
   void* alloc(size_t bytes);
   void free(void* p);

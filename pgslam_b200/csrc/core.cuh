@@ -58,7 +58,8 @@ struct Cloud {
   const Desc* find(const std::string& label) const { return const_cast<Cloud*>(this)->find(label); }
   Desc& add(const std::string& label, int span);  // (re)allocates span*n floats, zeroed
   void remove(const std::string& label);
-  std::unique_ptr<Cloud> clone() const;
+  // deep copy; `target` = the context (stream) the copy is made on and belongs to
+  std::unique_ptr<Cloud> clone(Ctx* target = nullptr) const;
 };
 
 void concatenate_cloud(Cloud& a, const Cloud& b);  // DP::concatenate

@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "knn.cuh"
 #include "solve.cuh"
@@ -1155,13 +1156,58 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
 void IcpEngine::run_batch(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
                           const double* T_inits, pgs_icp_result* results) {
   const int P = (int)readings.size();
+  // ---- large batches: sub-batches on worker streams ------------------------------
+  constexpr int kMinPairsPerStream = 4;
+  const int S = ctx_->profiling ? 1 : std::min(ctx_->batch_streams, P / kMinPairsPerStream);
+  if (S > 1) {
+    // everything queued so far on this context's stream (uploads, filters) happens first
+    if (!ctx_->fork_ev) PGS_CUDA(cudaEventCreateWithFlags(&ctx_->fork_ev, cudaEventDisableTiming));
+    PGS_CUDA(cudaEventRecord(ctx_->fork_ev, ctx_->stream));
+    std::vector<std::thread> threads;
+    std::vector<std::unique_ptr<Error>> errors(S);
+    for (int w = 0; w < S; ++w) {
+      Ctx* wc = ctx_->worker(w);
+      PGS_CUDA(cudaStreamWaitEvent(wc->stream, ctx_->fork_ev, 0));
+      threads.emplace_back([this, wc, w, S, P, &readings, &references, T_inits, results, &errors]() {
+        try {
+          PGS_CUDA(cudaSetDevice(wc->device));
+          // interleaved split: iteration counts vary per pair, neighbours share the load
+          std::vector<const Cloud*> rd, rf;
+          std::vector<double> Ti;
+          std::vector<int> which;
+          for (int p = w; p < P; p += S) {
+            which.push_back(p);
+            rd.push_back(readings[p]);
+            rf.push_back(references[p]);
+            if (T_inits) Ti.insert(Ti.end(), T_inits + 16 * p, T_inits + 16 * p + 16);
+          }
+          std::vector<pgs_icp_result> res(which.size());
+          IcpEngine sub(wc, cfg_);
+          sub.run_batch(rd, rf, T_inits ? Ti.data() : nullptr, res.data());
+          for (size_t j = 0; j < which.size(); ++j) results[which[j]] = res[j];
+        } catch (const Error& e) {
+          errors[w] = std::make_unique<Error>(e);
+        } catch (const std::exception& e) {
+          errors[w] = std::make_unique<Error>(PGS_CUDA_ERROR, e.what());
+        }
+      });
+    }
+    for (auto& t : threads) t.join();
+    for (int w = 0; w < S; ++w) {
+      ctx_->launches += ctx_->workers[w]->launches;
+      ctx_->workers[w]->launches = 0;
+    }
+    for (auto& e : errors)
+      if (e) throw *e;
+    return;  // every worker synchronised its stream before returning its results
+  }
   if (ctx_->profiling) {
     for (auto& e : idx_ev_)
       if (!e) PGS_CUDA(cudaEventCreate(&e));
     PGS_CUDA(cudaEventRecord(idx_ev_[0], ctx_->stream));
   }
   std::vector<std::unique_ptr<Cloud>> refs(P);
-  for (int p = 0; p < P; ++p) refs[p] = references[p]->clone();
+  for (int p = 0; p < P; ++p) refs[p] = references[p]->clone(ctx_);
   std::vector<std::unique_ptr<PreparedRef>> prepared;
   prepare_references(refs, false, prepared);
   if (ctx_->profiling) PGS_CUDA(cudaEventRecord(idx_ev_[1], ctx_->stream));
@@ -1202,7 +1248,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   // ---- reading side: copy, reading filters ---------------------------------
   std::vector<std::unique_ptr<Cloud>> rds(P);
   std::vector<Cloud*> rdp(P);
-  for (int p = 0; p < P; ++p) { rds[p] = readings[p]->clone(); rdp[p] = rds[p].get(); }
+  for (int p = 0; p < P; ++p) { rds[p] = readings[p]->clone(ctx); rdp[p] = rds[p].get(); }
   apply_filters(ctx, cfg_.reading_filters, rdp);
 
   // ---- initial state ---------------------------------------------------------
@@ -1421,6 +1467,8 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       t.match_ms += a;
       t.select_ms += b;
       t.accumulate_ms += c;
+      if (std::getenv("PGS_TRACE_LOOP"))
+        std::fprintf(stderr, "[pgs] iteration %zu: match %.3f ms, select %.3f ms, accumulate %.3f ms\n", i / 4, a, b, c);
     }
     for (auto& e : kev) cudaEventDestroy(e);
     for (auto& e : ev) cudaEventDestroy(e);

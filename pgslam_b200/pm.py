@@ -128,6 +128,7 @@ SIGNATURES = {
     "pgs_registrar_name": (C.c_char_p, [C.c_int, C.c_int]),
     "pgs_ctx_launch_count": (C.c_uint64, [_vp]),
     "pgs_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "pgs_ctx_set_batch_streams": (C.c_int, [_vp, C.c_int]),
     "pgs_ctx_last_stage_times": (C.c_int, [_vp, C.POINTER(StageTimes)]),
 }
 
@@ -213,6 +214,10 @@ class Context:
 
     def set_profiling(self, on: bool):
         self.lib.pgs_ctx_set_profiling(self.h, int(on))
+
+    def set_batch_streams(self, n: int):
+        """Worker streams a batch of independent pairs is split over (default 4)."""
+        self.check(self.lib.pgs_ctx_set_batch_streams(self.h, int(n)))
 
     def stage_times(self) -> dict:
         t = StageTimes()
