@@ -19,6 +19,7 @@ OK, CONVERGENCE_ERROR, TRANSFORMATION_ERROR, INVALID_PARAMETER, INVALID_FIELD = 
 
 F_RANDOM_SAMPLING, F_VOXEL_GRID, F_SURFACE_NORMAL, F_OBSERVATION_DIRECTION = 1, 2, 3, 4
 F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST, F_BOUNDING_BOX = 5, 6, 7, 8, 9
+F_MAX_DENSITY = 10
 O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST, O_SURFACE_NORMAL = 1, 2, 3, 4, 5
 E_POINT_TO_PLANE, E_POINT_TO_PLANE_WITH_COV, E_POINT_TO_POINT = 1, 2, 3
 MAX_MODS = 8
@@ -30,7 +31,8 @@ _dp = C.POINTER(C.c_double)
 
 class CCloud(C.Structure):
     _fields_ = [("n", C.c_int64), ("feat", _fp), ("normals", _fp), ("obsdir", _fp),
-                ("noise", _fp), ("dens", _fp), ("eigval", _fp), ("eigvec", _fp)]
+                ("noise", _fp), ("dens", _fp), ("eigval", _fp), ("eigvec", _fp),
+                ("meandist", _fp), ("matched", _fp), ("matched_span", C.c_int)]
 
 
 class CFilter(C.Structure):
@@ -144,10 +146,13 @@ def _d(a):
     return a.ctypes.data_as(_dp)
 
 
-_DESC = (("normals", 3), ("obsdir", 3), ("noise", 1), ("dens", 1), ("eigval", 3), ("eigvec", 9))
+# span None = variable (stored beside the pointer as <field>_span)
+_DESC = (("normals", 3), ("obsdir", 3), ("noise", 1), ("dens", 1), ("eigval", 3), ("eigvec", 9),
+         ("meandist", 1), ("matched", None))
 # PM label <-> oracle field
 LABEL_OF = {"normals": "normals", "obsdir": "observationDirections", "noise": "simpleSensorNoise",
-            "dens": "densities", "eigval": "eigValues", "eigvec": "eigVectors"}
+            "dens": "densities", "eigval": "eigValues", "eigvec": "eigVectors",
+            "meandist": "meanDists", "matched": "matchedIds"}
 FIELD_OF = {v: k for k, v in LABEL_OF.items()}
 
 
@@ -170,6 +175,9 @@ class Cloud:
 
     def set_desc(self, field, arr):
         span = dict(_DESC)[field]
+        if span is None:
+            span = np.asarray(arr).shape[0]
+            setattr(self.ptr.contents, field + "_span", span)
         arr = np.ascontiguousarray(np.asarray(arr, dtype=np.float32).reshape(span, -1).T).ravel()
         libc = C.CDLL(None)
         libc.malloc.restype = C.c_void_p
@@ -193,6 +201,8 @@ class Cloud:
 
     def desc(self, field):
         span = dict(_DESC)[field]
+        if span is None:
+            span = getattr(self.ptr.contents, field + "_span")
         p = getattr(self.ptr.contents, field)
         if not p:
             return None
@@ -250,7 +260,9 @@ def make_filter(name: str, **p) -> CFilter:
         f.type, f.i0 = F_SURFACE_NORMAL, int(p.get("knn", 5))
         f.p0 = float(p.get("maxDist", np.inf))
         f.i1 = (int(p.get("keepNormals", 1)) | int(p.get("keepDensities", 0)) << 1 |
-                int(p.get("keepEigenValues", 0)) << 2 | int(p.get("keepEigenVectors", 0)) << 3)
+                int(p.get("keepEigenValues", 0)) << 2 | int(p.get("keepEigenVectors", 0)) << 3 |
+                int(p.get("keepMatchedIds", 0)) << 4 | int(p.get("keepMeanDist", 0)) << 5 |
+                int(p.get("sortEigen", 0)) << 6)
     elif name == "ObservationDirectionDataPointsFilter":
         f.type = F_OBSERVATION_DIRECTION
         f.p0, f.p1, f.p2 = (float(p.get(k, 0.0)) for k in ("x", "y", "z"))
@@ -262,6 +274,8 @@ def make_filter(name: str, **p) -> CFilter:
         f.type, f.i0, f.p0 = F_MAX_DIST, int(p.get("dim", -1)), float(p.get("maxDist", 1.0))
     elif name == "MinDistDataPointsFilter":
         f.type, f.i0, f.p0 = F_MIN_DIST, int(p.get("dim", -1)), float(p.get("minDist", 1.0))
+    elif name == "MaxDensityDataPointsFilter":
+        f.type, f.p0, f.i0 = F_MAX_DENSITY, float(p.get("maxDensity", 10.0)), int(p.get("seed", 0))
     elif name == "BoundingBoxDataPointsFilter":
         f.type, f.i0 = F_BOUNDING_BOX, int(p.get("removeInside", 1))
         for j, (key, dflt) in enumerate((("xMin", -1), ("xMax", 1), ("yMin", -1), ("yMax", 1), ("zMin", -1), ("zMax", 1))):

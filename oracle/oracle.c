@@ -76,13 +76,16 @@ orc_cloud *orc_cloud_copy(const orc_cloud *c) {
   o->dens = dup_f(c->dens, n);
   o->eigval = dup_f(c->eigval, 3 * n);
   o->eigvec = dup_f(c->eigvec, 9 * n);
+  o->meandist = dup_f(c->meandist, n);
+  o->matched = dup_f(c->matched, (size_t)c->matched_span * n);
+  o->matched_span = c->matched_span;
   return o;
 }
 
 void orc_cloud_free(orc_cloud *c) {
   if (!c) return;
   free(c->feat); free(c->normals); free(c->obsdir); free(c->noise);
-  free(c->dens); free(c->eigval); free(c->eigvec);
+  free(c->dens); free(c->eigval); free(c->eigvec); free(c->meandist); free(c->matched);
   free(c);
 }
 
@@ -107,6 +110,10 @@ void orc_cloud_concatenate(orc_cloud *a, const orc_cloud *b) {
   cat_desc(&a->dens, na, b->dens, nb, 1);
   cat_desc(&a->eigval, na, b->eigval, nb, 3);
   cat_desc(&a->eigvec, na, b->eigvec, nb, 9);
+  cat_desc(&a->meandist, na, b->meandist, nb, 1);
+  /* same name but different span: not the same descriptor -> dropped */
+  cat_desc(&a->matched, na, a->matched_span == b->matched_span ? b->matched : NULL, nb, a->matched_span);
+  if (!a->matched) a->matched_span = 0;
   a->n = na + nb;
 }
 
@@ -120,7 +127,7 @@ static void cloud_select(orc_cloud *c, const int64_t *idx, int64_t m) {
                 (span) * sizeof(float));                                   \
   }
   SEL(feat, 4) SEL(normals, 3) SEL(obsdir, 3) SEL(noise, 1) SEL(dens, 1)
-  SEL(eigval, 3) SEL(eigvec, 9)
+  SEL(eigval, 3) SEL(eigvec, 9) SEL(meandist, 1) SEL(matched, c->matched_span)
 #undef SEL
   c->n = m;
 }
@@ -716,6 +723,7 @@ static int filter_voxel_grid(const orc_filter *f, orc_cloud *c) {
     }
     if (avg_desc) {
       AVG(normals, 3) AVG(obsdir, 3) AVG(noise, 1) AVG(dens, 1) AVG(eigval, 3) AVG(eigvec, 9)
+      AVG(meandist, 1) AVG(matched, c->matched_span)
     }
 #undef AVG
     firsts[m++] = first;
@@ -743,6 +751,14 @@ static int filter_surface_normal(const orc_filter *f, orc_cloud *c) {
   if (flags & 2) { free(c->dens); c->dens = (float *)calloc((size_t)(n + 1), sizeof(float)); }
   if (flags & 4) { free(c->eigval); c->eigval = (float *)calloc((size_t)(n + 1) * 3, sizeof(float)); }
   if (flags & 8) { free(c->eigvec); c->eigvec = (float *)calloc((size_t)(n + 1) * 9, sizeof(float)); }
+  if (flags & 16) {
+    /* keepMatchedIds: the k x N ids cast to T (unfound -> -1)                */
+    free(c->matched);
+    c->matched = (float *)calloc((size_t)(n + 1) * k, sizeof(float));
+    c->matched_span = k;
+    for (int64_t m = 0; m < n * k; ++m) c->matched[m] = (float)ids[m];
+  }
+  if (flags & 32) { free(c->meandist); c->meandist = (float *)calloc((size_t)(n + 1), sizeof(float)); }
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
     double mean[3] = {0, 0, 0};
@@ -771,8 +787,32 @@ static int filter_surface_normal(const orc_filter *f, orc_cloud *c) {
     C[0] = C[0] / (double)real; C[1] = C[1] / (double)real; C[2] = C[2] / (double)real;
     C[4] = C[4] / (double)real; C[5] = C[5] / (double)real; C[8] = C[8] / (double)real;
     C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+    if (flags & 32) {
+      /* keepMeanDist: distance from the point to the mean of its neighbours
+       * [UPSTREAM-RECALLED, SurfaceNormal.cpp: (point - mean).norm()]         */
+      double ex = (double)c->feat[4 * i + 0] - mean[0];
+      double ey = (double)c->feat[4 * i + 1] - mean[1];
+      double ez = (double)c->feat[4 * i + 2] - mean[2];
+      c->meandist[i] = (float)sqrt(ex * ex + ey * ey + ez * ez);
+    }
     double w[3], V[9];
     orc_eig3_sym(C, w, V);
+    if (flags & 64) {
+      /* sortEigen: eigenvalues ascending, eigenvectors permuted with them
+       * (stable: equal values keep their order)                              */
+      int ord[3] = {0, 1, 2};
+      for (int a = 1; a < 3; ++a)
+        for (int b2 = a; b2 > 0 && w[ord[b2]] < w[ord[b2 - 1]]; --b2) {
+          int tmp = ord[b2]; ord[b2] = ord[b2 - 1]; ord[b2 - 1] = tmp;
+        }
+      double w2[3], V2[9];
+      for (int e = 0; e < 3; ++e) {
+        w2[e] = w[ord[e]];
+        for (int d = 0; d < 3; ++d) V2[e * 3 + d] = V[ord[e] * 3 + d];
+      }
+      memcpy(w, w2, sizeof(w));
+      memcpy(V, V2, sizeof(V));
+    }
     /* rank test (A.9): need rank(C) >= 2; threshold 3*eps_T relative       */
     double wmax = w[0] > w[1] ? w[0] : w[1];
     if (w[2] > wmax) wmax = w[2];
@@ -903,8 +943,43 @@ static int filter_bounding_box(const orc_filter *f, orc_cloud *c) {
   return ORC_OK;
 }
 
+static int filter_max_density(const orc_filter *f, orc_cloud *c) {
+  /* MaxDensityDataPointsFilter [UPSTREAM-RECALLED, DataPointsFilters/MaxDensity.cpp]:
+   * a point denser than maxDensity survives with probability maxDensity/density;
+   * points at the saturation value (the cloud's maximum density) have that
+   * probability multiplied by (1 - nbSaturated/nbPoints) in INTEGER arithmetic,
+   * i.e. by 1 unless every point is saturated (then 0).  rand() -> counter hash (H7). */
+  if (!c->dens) return ORC_INVALID_FIELD;
+  float max_density = (float)f->p0;
+  int64_t n = c->n;
+  float last = -INFINITY;
+  for (int64_t i = 0; i < n; ++i)
+    if (c->dens[i] > last) last = c->dens[i];
+  int64_t saturated = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (c->dens[i] == last) ++saturated;
+  float sat_factor = (float)(1 - (n > 0 ? saturated / n : 0));
+  int64_t *keep = (int64_t *)malloc((size_t)(n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    float density = c->dens[i];
+    if (density > max_density) {
+      float r = hash_uniform((uint64_t)f->i0, (uint64_t)i);
+      float accept = max_density / density;
+      if (density == last) accept = accept * sat_factor;
+      if (r < accept) keep[m++] = i;
+    } else {
+      keep[m++] = i;
+    }
+  }
+  cloud_select(c, keep, m);
+  free(keep);
+  return ORC_OK;
+}
+
 int orc_filter_apply(const orc_filter *f, orc_cloud *c) {
   switch (f->type) {
+    case ORC_F_MAX_DENSITY: return filter_max_density(f, c);
     case ORC_F_BOUNDING_BOX: return filter_bounding_box(f, c);
     case ORC_F_RANDOM_SAMPLING: return filter_random_sampling(f, c);
     case ORC_F_VOXEL_GRID: return filter_voxel_grid(f, c);

@@ -51,6 +51,9 @@ typedef struct {
   float *dens;     /* n   or NULL  ("densities")                           */
   float *eigval;   /* 3*n or NULL  ("eigValues")                           */
   float *eigvec;   /* 9*n or NULL  ("eigVectors", column-major 3x3)        */
+  float *meandist; /* n   or NULL  ("meanDists")                           */
+  float *matched;  /* matched_span*n or NULL ("matchedIds", ids as floats) */
+  int matched_span;
 } orc_cloud;
 
 orc_cloud *orc_cloud_new(int64_t n);
@@ -77,13 +80,15 @@ enum {
   ORC_F_RANDOM_SAMPLING = 1, /* p0 = prob, i0 = seed                        */
   ORC_F_VOXEL_GRID = 2,      /* p0,p1,p2 = vSize, i0 = useCentroid, i1 = avgDesc */
   ORC_F_SURFACE_NORMAL = 3,  /* i0 = knn, p0 = maxDist, i1 flags (bit0 normals,
-                                bit1 densities, bit2 eigValues, bit3 eigVectors) */
+                                bit1 densities, bit2 eigValues, bit3 eigVectors,
+                                bit4 matchedIds, bit5 meanDists, bit6 sortEigen) */
   ORC_F_OBSERVATION_DIRECTION = 4, /* p0,p1,p2 = sensor position            */
   ORC_F_ORIENT_NORMALS = 5,  /* i0 = towardCenter                           */
   ORC_F_SIMPLE_SENSOR_NOISE = 6, /* i0 = sensorType, p0 = gain              */
   ORC_F_MAX_DIST = 7,        /* i0 = dim (-1 radial), p0 = maxDist          */
   ORC_F_MIN_DIST = 8,        /* i0 = dim (-1 radial), p0 = minDist          */
-  ORC_F_BOUNDING_BOX = 9     /* box[6] = xMin,xMax,yMin,yMax,zMin,zMax; i0 = removeInside */
+  ORC_F_BOUNDING_BOX = 9,    /* box[6] = xMin,xMax,yMin,yMax,zMin,zMax; i0 = removeInside */
+  ORC_F_MAX_DENSITY = 10     /* p0 = maxDensity, i0 = seed; needs `densities` */
 };
 typedef struct {
   int type;

@@ -96,6 +96,40 @@ random_keep_kernel(int* __restrict__ keep, int n, uint64_t seed, float prob) {
   keep[i] = r < prob;
 }
 
+// MaxDensityDataPointsFilter: maximum density and how many points sit on it, then the
+// keep decision (same counter-based uniform as RandomSampling)
+__global__ void __launch_bounds__(256) density_max_kernel(const float* __restrict__ dens, int n, unsigned* __restrict__ out) {
+  unsigned m = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, f2ord(dens[i]));
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+__global__ void __launch_bounds__(256) density_count_kernel(const float* __restrict__ dens, int n, unsigned* __restrict__ io) {
+  const float last = ord2f(io[0]);
+  unsigned c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += dens[i] == last;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(io + 1, c);
+}
+__global__ void __launch_bounds__(256)
+density_keep_kernel(const float* __restrict__ dens, int* __restrict__ keep, int n, float max_density, uint64_t seed,
+                    const unsigned* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float last = ord2f(stats[0]);
+  const float sat_factor = (float)(1 - (int)(stats[1] / (unsigned)n));
+  const float density = dens[i];
+  bool k = true;
+  if (density > max_density) {
+    uint64_t h = splitmix64(splitmix64(seed) ^ ((uint64_t)i * 0xD1B54A32D192ED03ull));
+    float r = __fmul_rn((float)(h >> 40), 1.0f / 16777216.0f);
+    float accept = __fdiv_rn(max_density, density);
+    if (density == last) accept = __fmul_rn(accept, sat_factor);
+    k = r < accept;
+  }
+  keep[i] = k;
+}
+
 __global__ void __launch_bounds__(256)
 dist_keep_kernel(const float4* __restrict__ feat, int* __restrict__ keep, int n, int dim, float lim, int is_max) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,6 +170,9 @@ struct NormalJob {
   float* dens;     // n or null
   float* eigval;   // 3n or null
   float* eigvec;   // 9n or null
+  float* matched;  // k*n or null ("matchedIds": the neighbour ids as floats)
+  float* meandist; // n or null   ("meanDists": |point - mean of its neighbours|)
+  int sort_eigen;  // eigenvalues ascending, eigenvectors permuted with them
 };
 
 __global__ void __launch_bounds__(128)
@@ -144,6 +181,8 @@ normals_kernel(const NormalJob* __restrict__ jobs, int k) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= job.n) return;
   const int32_t* nb = job.ids + (size_t)i * k;
+  if (job.matched)
+    for (int j = 0; j < k; ++j) job.matched[(size_t)i * k + j] = (float)nb[j];
   double mean[3] = {0.0, 0.0, 0.0};
   int real = 0;
   for (int j = 0; j < k; ++j) {
@@ -170,8 +209,27 @@ normals_kernel(const NormalJob* __restrict__ jobs, int k) {
   C[0] = C[0] / (double)real; C[1] = C[1] / (double)real; C[2] = C[2] / (double)real;
   C[4] = C[4] / (double)real; C[5] = C[5] / (double)real; C[8] = C[8] / (double)real;
   C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  if (job.meandist) {
+    const float4 me = job.feat[i];
+    const double ex = (double)me.x - mean[0], ey = (double)me.y - mean[1], ez = (double)me.z - mean[2];
+    job.meandist[i] = (float)sqrt(ex * ex + ey * ey + ez * ez);
+  }
   double w[3], V[9];
   jacobi_sym<3>(C, w, V);
+  if (job.sort_eigen) {
+    int ord[3] = {0, 1, 2};
+    for (int a = 1; a < 3; ++a)
+      for (int b = a; b > 0 && w[ord[b]] < w[ord[b - 1]]; --b) {
+        const int t = ord[b]; ord[b] = ord[b - 1]; ord[b - 1] = t;
+      }
+    double w2[3], V2[9];
+    for (int e = 0; e < 3; ++e) {
+      w2[e] = w[ord[e]];
+      for (int d = 0; d < 3; ++d) V2[e * 3 + d] = V[ord[e] * 3 + d];
+    }
+    for (int e = 0; e < 3; ++e) w[e] = w2[e];
+    for (int e = 0; e < 9; ++e) V[e] = V2[e];
+  }
   double wmax = w[0] > w[1] ? w[0] : w[1];
   if (w[2] > wmax) wmax = w[2];
   int rank = 0;
@@ -367,9 +425,11 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   const int k = (int)m.integer("knn");
   if (k > 32) throw Error(PGS_INVALID_PARAMETER, "SurfaceNormalDataPointsFilter: knn > 32 is not supported");
   const float max_dist = (float)m.real("maxDist");
-  if (m.flag("keepMatchedIds") || m.flag("keepMeanDist") || m.flag("sortEigen") || m.flag("smoothNormals"))
-    throw Error(PGS_INVALID_PARAMETER,
-                "SurfaceNormalDataPointsFilter: keepMatchedIds/keepMeanDist/sortEigen/smoothNormals are not supported");
+  // upstream smooths in place, point after point, so every normal depends on the already
+  // smoothed normals of lower-indexed neighbours: an order-dependent recurrence with no
+  // parallel statement that reproduces it
+  if (m.flag("smoothNormals"))
+    throw Error(PGS_INVALID_PARAMETER, "SurfaceNormalDataPointsFilter: smoothNormals is not supported");
   const int B = (int)clouds.size();
   std::vector<int> ns(B);
   for (int b = 0; b < B; ++b) ns[b] = (int)clouds[b]->n;
@@ -390,16 +450,21 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   int max_n = 0;
   for (int b = 0; b < B; ++b) {
     Cloud& c = *clouds[b];
-    NormalJob j{c.feat.p, ids[b].p, ns[b], nullptr, nullptr, nullptr, nullptr};
+    NormalJob j{c.feat.p, ids[b].p, ns[b], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                m.flag("sortEigen") ? 1 : 0};
     if (m.flag("keepNormals")) j.normals = c.add("normals", 3).data.p;
     if (m.flag("keepDensities")) j.dens = c.add("densities", 1).data.p;
     if (m.flag("keepEigenValues")) j.eigval = c.add("eigValues", 3).data.p;
     if (m.flag("keepEigenVectors")) j.eigvec = c.add("eigVectors", 9).data.p;
+    if (m.flag("keepMatchedIds")) j.matched = c.add("matchedIds", k).data.p;
+    if (m.flag("keepMeanDist")) j.meandist = c.add("meanDists", 1).data.p;
     // Desc vectors may reallocate on add(): re-read the pointers afterwards
     if (j.normals) j.normals = c.find("normals")->data.p;
     if (j.dens) j.dens = c.find("densities")->data.p;
     if (j.eigval) j.eigval = c.find("eigValues")->data.p;
     if (j.eigvec) j.eigvec = c.find("eigVectors")->data.p;
+    if (j.matched) j.matched = c.find("matchedIds")->data.p;
+    if (j.meandist) j.meandist = c.find("meanDists")->data.p;
     jobs[b] = j;
     max_n = std::max(max_n, ns[b]);
   }
@@ -468,6 +533,21 @@ void apply_filter(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
       DBuf<int> keep(ctx, n);
       random_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(keep.p, n, (uint64_t)m.integer("seed"), (float)m.real("prob"));
       ctx_count_launches(ctx, 1);
+      compact_cloud(c, keep.p);
+      continue;
+    } else if (name == "MaxDensityDataPointsFilter") {
+      Desc* dn = c.find("densities");
+      if (!dn) throw Error(PGS_INVALID_FIELD, "MaxDensityDataPointsFilter: Error, no densities found in descriptors.");
+      if (!n) continue;
+      DBuf<int> keep(ctx, n);
+      DBuf<unsigned> stats(ctx, 2);
+      stats.zero();
+      const int nb = std::min(ceil_div(n, 1024), 256);
+      density_max_kernel<<<nb, 256, 0, s>>>(dn->data.p, n, stats.p);
+      density_count_kernel<<<nb, 256, 0, s>>>(dn->data.p, n, stats.p);
+      density_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(dn->data.p, keep.p, n, (float)m.real("maxDensity"),
+                                                           (uint64_t)m.integer("seed"), stats.p);
+      ctx_count_launches(ctx, 3);
       compact_cloud(c, keep.p);
       continue;
     } else if (name == "BoundingBoxDataPointsFilter") {

@@ -62,6 +62,9 @@ const std::vector<ModuleDoc>& registry() {
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"maxDist", "", "1", NINF, INF, 'f'}}},
       {Kind::DataPointsFilter, "MinDistDataPointsFilter",
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"minDist", "", "1", NINF, INF, 'f'}}},
+      {Kind::DataPointsFilter, "MaxDensityDataPointsFilter",
+       {{"maxDensity", "points denser than this are subsampled towards it", "10", "0.0000001", INF, 'f'},
+        {"seed", "seed of the counter-based generator (SURVEY H7)", "0", "0", "", 'i'}}},
       {Kind::DataPointsFilter, "BoundingBoxDataPointsFilter",
        {{"xMin", "", "-1", NINF, INF, 'f'}, {"xMax", "", "1", NINF, INF, 'f'},
         {"yMin", "", "-1", NINF, INF, 'f'}, {"yMax", "", "1", NINF, INF, 'f'},

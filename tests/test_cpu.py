@@ -341,6 +341,31 @@ def test_oracle_icp_with_knn_3_and_step_filters():
     assert np.abs(s1["T"][:3, 3] - truth[:3, 3]).max() < 0.05
 
 
+def test_oracle_surface_normal_optional_descriptors():
+    """keepMatchedIds / keepMeanDist / sortEigen against numpy on the same neighbourhoods."""
+    _, rf, _ = synth.scan_pair(23, beams=16, az_steps=120)
+    k = 7
+    c = ob.Cloud(rf)
+    assert ob.apply_filter(c, "SurfaceNormalDataPointsFilter", knn=k, keepEigenValues=1, keepEigenVectors=1,
+                           keepMatchedIds=1, keepMeanDist=1, sortEigen=1) == 0
+    ids, _ = ob.kdtree_knn(rf, rf, k=k)
+    got = c.descriptors()
+    assert np.array_equal(got["matchedIds"], ids.astype(np.float32))
+    P = rf[:3].astype(np.float64)
+    mean = P[:, ids].mean(axis=1)  # 3 x N
+    np.testing.assert_allclose(got["meanDists"][0], np.linalg.norm(P - mean, axis=0), rtol=1e-6, atol=1e-7)
+    ev = got["eigValues"]
+    assert (np.diff(ev, axis=0) >= 0).all()  # ascending
+    # the normal is the first (smallest) eigenvector after sorting
+    np.testing.assert_array_equal(got["normals"], np.clip(got["eigVectors"][:3], -1, 1))
+    # and it is an eigen-decomposition of the neighbourhood covariance
+    i = 100
+    Q = P[:, ids[:, i]] - mean[:, [i]]
+    Cm = Q @ Q.T / k
+    V = got["eigVectors"][:, i].reshape(3, 3).T.astype(np.float64)  # columns = eigenvectors
+    np.testing.assert_allclose(Cm @ V, V * ev[:, i].astype(np.float64), atol=1e-6)
+
+
 def test_oracle_icp_is_equivariant_under_a_common_rigid_motion():
     rd, rf, _ = synth.scan_pair(10, beams=16, az_steps=300)
     G = synth.pose_matrix([1.0, -2.0, 0.3], 0.4, 0.0, 0.0)

@@ -114,9 +114,12 @@ def _cmp_cloud(dp, oc, exact=True):
             np.testing.assert_allclose(got[lab], want[lab], rtol=1e-6, atol=1e-7, err_msg=lab)
 
 
-def test_surface_normal_filter_bit_exact(pm, pair30k):
+@pytest.mark.parametrize("extra", [{}, {"keepMatchedIds": 1, "keepMeanDist": 1, "sortEigen": 1},
+                                   {"knn": 5, "maxDist": 0.3, "keepMatchedIds": 1, "keepMeanDist": 1}])
+def test_surface_normal_filter_bit_exact(pm, pair30k, extra):
     _, rf, _ = pair30k
     params = {"knn": 10, "keepNormals": 1, "keepDensities": 1, "keepEigenValues": 1, "keepEigenVectors": 1}
+    params.update(extra)
     dp = pm.DataPoints(rf)
     f = pm.DataPointsFilters()
     f.append("SurfaceNormalDataPointsFilter", params)
@@ -169,6 +172,24 @@ def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
     assert ob.apply_filter(oc, name, **params) == 0
     assert 0 < oc.n < rd.shape[1]
     _cmp_cloud(dp, oc)
+
+
+def test_max_density_filter_bit_exact(pm, pair30k):
+    rd, _, _ = pair30k
+    chain = [{"SurfaceNormalDataPointsFilter": {"knn": 8, "keepDensities": 1}},
+             {"MaxDensityDataPointsFilter": {"maxDensity": 50.0, "seed": 3}}]
+    dp = pm.DataPoints(rd)
+    pm.DataPointsFilters(util.to_yaml(chain)).apply(dp)
+    oc = ob.Cloud(rd)
+    for it in chain:
+        (name, p), = ob._modlist([it])
+        assert ob.apply_filter(oc, name, **p) == 0
+    assert 0 < oc.n < rd.shape[1]
+    _cmp_cloud(dp, oc)
+    # no densities -> InvalidField, as upstream
+    with pytest.raises(pm.InvalidField):
+        pm.DataPointsFilters(util.to_yaml(chain[1:])).apply(pm.DataPoints(rd))
+    assert ob.apply_filter(ob.Cloud(rd), "MaxDensityDataPointsFilter") == ob.INVALID_FIELD
 
 
 def test_rigid_transformation_bit_exact_and_rigidity_check(pm, pair30k):
