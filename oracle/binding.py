@@ -21,6 +21,7 @@ F_RANDOM_SAMPLING, F_VOXEL_GRID, F_SURFACE_NORMAL, F_OBSERVATION_DIRECTION = 1, 
 F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST, F_BOUNDING_BOX = 5, 6, 7, 8, 9
 F_MAX_DENSITY = 10
 O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST, O_SURFACE_NORMAL = 1, 2, 3, 4, 5
+O_VAR_TRIMMED_DIST = 6
 E_POINT_TO_PLANE, E_POINT_TO_PLANE_WITH_COV, E_POINT_TO_POINT = 1, 2, 3
 MAX_MODS = 8
 
@@ -41,7 +42,7 @@ class CFilter(C.Structure):
 
 
 class COutlier(C.Structure):
-    _fields_ = [("type", C.c_int), ("p0", C.c_double)]
+    _fields_ = [("type", C.c_int), ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double)]
 
 
 class CMinOut(C.Structure):
@@ -109,6 +110,7 @@ def lib():
     L.orc_rigid_transform.argtypes = [cp, _dp]
     L.orc_outlier_weights.argtypes = [C.POINTER(COutlier), C.c_int, _fp, C.c_int64, _fp]
     L.orc_dists_quantile.argtypes = [_fp, C.c_int64, C.c_double, _fp]
+    L.orc_var_trimmed_ratio.argtypes = [_fp, C.c_int64, C.c_double, C.c_double, C.c_double, _fp]
     L.orc_outlier_weights_full.argtypes = [C.POINTER(COutlier), C.c_int, cp, cp, _ip, _fp, C.c_int, _fp]
     L.orc_minimize.argtypes = [C.c_int, C.c_double, cp, cp, _ip, _fp, _fp, C.c_int, C.POINTER(CMinOut)]
     L.orc_minimize_ex.argtypes = [C.c_int, C.c_int, C.c_double, cp, cp, _ip, _fp, _fp, C.c_int, C.POINTER(CMinOut)]
@@ -297,6 +299,9 @@ def make_outlier(name: str, **p) -> COutlier:
         o.type, o.p0 = O_MEDIAN_DIST, float(p.get("factor", 3.0))
     elif name == "SurfaceNormalOutlierFilter":
         o.type, o.p0 = O_SURFACE_NORMAL, float(p.get("maxAngle", 1.57))
+    elif name == "VarTrimmedDistOutlierFilter":
+        o.type = O_VAR_TRIMMED_DIST
+        o.p0, o.p1, o.p2 = float(p.get("minRatio", 0.05)), float(p.get("maxRatio", 0.99)), float(p.get("lambda", 0.95))
     else:
         raise KeyError(name)
     return o

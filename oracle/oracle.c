@@ -1038,6 +1038,45 @@ int orc_dists_quantile(const float *d2, int64_t nk, double q, float *out) {
   return ORC_OK;
 }
 
+/* VarTrimmedDistOutlierFilter::optimizeInlierRatio [UPSTREAM-RECALLED,
+ * OutlierFiltersImpl.cpp; Phillips et al., "Outlier robust ICP for minimizing
+ * fractional RMSD"]: over the sorted valid squared distances s_1 <= ... <= s_M,
+ *     FRMS(j) = (1 / (j/N)^lambda)^2 * (1/j) * (s_1 + ... + s_j),   N = k x N_r,
+ * minimised over j in (floor(minRatio N), floor(maxRatio N)]; the optimal ratio is
+ * (float)(j* - 1) / (float)N and the weight test is dist <= quantile(ratio).
+ * Stated deviations: the running sum and FRMS are fp64 (upstream: T, in a
+ * sequential order no parallel scan reproduces -- same rule as H4/H9), and the
+ * range is clamped to the M valid distances (upstream reads past them when some
+ * matches are invalid).                                                     */
+int orc_var_trimmed_ratio(const float *d2, int64_t nk, double min_ratio, double max_ratio,
+                          double lambda, float *ratio) {
+  float *vals = (float *)malloc((size_t)(nk + 1) * sizeof(float));
+  int64_t m = 0;
+  for (int64_t i = 0; i < nk; ++i)
+    if (!isinf(d2[i]) && d2[i] > 0.f) vals[m++] = d2[i];
+  if (m == 0) { free(vals); return ORC_CONVERGENCE_ERROR; }
+  qsort(vals, (size_t)m, sizeof(float), cmp_f32);
+  int64_t min_el = (int64_t)floorf((float)min_ratio * (float)nk);
+  int64_t max_el = (int64_t)floorf((float)max_ratio * (float)nk);
+  if (max_el > m) max_el = m;
+  if (min_el > max_el - 1) min_el = max_el - 1;
+  if (min_el < 0) min_el = 0;
+  double cum = 0.0, best = INFINITY;
+  int64_t best_j = min_el;
+  for (int64_t j = 0; j < max_el; ++j) {
+    cum += (double)vals[j];
+    if (j < min_el) continue;
+    double id = (double)(j + 1);
+    double deno = pow(id / (double)nk, lambda);
+    double inv = 1.0 / deno;
+    double frms = inv * inv * (1.0 / id) * cum;
+    if (frms < best) { best = frms; best_j = j; }
+  }
+  *ratio = (float)best_j / (float)nk;
+  free(vals);
+  return ORC_OK;
+}
+
 int orc_outlier_weights(const orc_outlier *o, int no, const float *d2, int64_t nk, float *w) {
   if (no == 0) {
     for (int64_t i = 0; i < nk; ++i) w[i] = isinf(d2[i]) ? 0.f : 1.f;
@@ -1061,6 +1100,15 @@ int orc_outlier_weights(const orc_outlier *o, int no, const float *d2, int64_t n
         limit = (float)o[f].p0 * (float)o[f].p0;
         for (int64_t i = 0; i < nk; ++i) w[i] *= (d2[i] >= limit) ? 1.f : 0.f;
         break;
+      case ORC_O_VAR_TRIMMED_DIST: {
+        float ratio = 0.f;
+        st = orc_var_trimmed_ratio(d2, nk, o[f].p0, o[f].p1, o[f].p2, &ratio);
+        if (st) return st;
+        st = orc_dists_quantile(d2, nk, (double)ratio, &limit);
+        if (st) return st;
+        for (int64_t i = 0; i < nk; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
+        break;
+      }
       case ORC_O_MEDIAN_DIST:
         st = orc_dists_quantile(d2, nk, 0.5, &limit);
         if (st) return st;

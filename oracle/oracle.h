@@ -109,12 +109,17 @@ enum {
   ORC_O_MAX_DIST = 2,     /* p0 = maxDist */
   ORC_O_MIN_DIST = 3,     /* p0 = minDist */
   ORC_O_MEDIAN_DIST = 4,  /* p0 = factor  */
-  ORC_O_SURFACE_NORMAL = 5 /* p0 = maxAngle: needs `normals` on both clouds */
+  ORC_O_SURFACE_NORMAL = 5, /* p0 = maxAngle: needs `normals` on both clouds */
+  ORC_O_VAR_TRIMMED_DIST = 6 /* p0 = minRatio, p1 = maxRatio, p2 = lambda   */
 };
 typedef struct {
   int type;
-  double p0;
+  double p0, p1, p2;
 } orc_outlier;
+/* VarTrimmedDistOutlierFilter::optimizeInlierRatio: the ratio minimising the
+ * FRMS criterion over the sorted valid distances (as a float).             */
+int orc_var_trimmed_ratio(const float *d2, int64_t nk, double min_ratio, double max_ratio,
+                          double lambda, float *ratio);
 /* weights k x n; returns ORC_CONVERGENCE_ERROR on "no outlier to filter".  */
 int orc_outlier_weights(const orc_outlier *o, int no, const float *d2,
                         int64_t nk, float *w);

@@ -599,6 +599,138 @@ void launch_match_k(int k, dim3 grid, cudaStream_t s, const PairView* views, Pai
   else match_k_kernel<32><<<grid, 128, 0, s>>>(views, states, maxr2, k);
 }
 
+// ---------------------------------------------------------------------------
+// VarTrimmedDistOutlierFilter (optimizeInlierRatio): sort the valid squared
+// distances (batched radix sort, invalid ones keyed to the end), then one block
+// per pair runs the fp64 running sum and the FRMS criterion
+//     FRMS(j) = (1 / (j/N)^lambda)^2 * (1/j) * (s_1 + ... + s_j)
+// over j in (floor(minRatio N), floor(maxRatio N)], takes the first minimum and
+// reads the quantile at the optimised ratio straight from the sorted array.
+// ---------------------------------------------------------------------------
+struct VarIn {
+  const float* d2;
+  int n;              // k x N_r
+  const int* active;  // null = always
+};
+
+__global__ void __launch_bounds__(256)
+var_keys_kernel(const VarIn* __restrict__ in, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int stride) {
+  const VarIn job = in[blockIdx.y];
+  if (job.active && !*job.active) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= job.n) return;
+  const unsigned u = __float_as_uint(job.d2[i]);
+  const bool valid = (u != 0u) && (u < 0x7f800000u);  // dist > 0 and dist != inf
+  keys[(size_t)blockIdx.y * stride + i] = valid ? u : 0xffffffffu;
+  vals[(size_t)blockIdx.y * stride + i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(1024)
+var_limit_kernel(const VarIn* __restrict__ in, const uint32_t* __restrict__ sorted, int stride, float min_ratio,
+                 float max_ratio, double lambda, float* __restrict__ limit_out, int* __restrict__ fail_out) {
+  __shared__ double warp_tot[32];
+  __shared__ double best_v[32];
+  __shared__ int best_i[32];
+  __shared__ int s_M;
+  const VarIn job = in[blockIdx.x];
+  if (job.active && !*job.active) return;
+  const uint32_t* __restrict__ s = sorted + (size_t)blockIdx.x * stride;
+  const int n = job.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {  // number of valid distances: first position holding the invalid key
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s[mid] == 0xffffffffu) hi = mid; else lo = mid + 1;
+    }
+    s_M = lo;
+  }
+  __syncthreads();
+  const int M = s_M;
+  if (M == 0) {
+    if (tid == 0) { fail_out[blockIdx.x] = 1; limit_out[blockIdx.x] = 0.f; }
+    return;
+  }
+  int min_el = (int)floorf(__fmul_rn(min_ratio, (float)n));
+  int max_el = (int)floorf(__fmul_rn(max_ratio, (float)n));
+  if (max_el > M) max_el = M;
+  if (min_el > max_el - 1) min_el = max_el - 1;
+  if (min_el < 0) min_el = 0;
+  const int chunk = (max_el + 1023) / 1024;
+  const int j0 = min(tid * chunk, max_el), j1 = min(j0 + chunk, max_el);
+  double sum = 0.0;
+  for (int j = j0; j < j1; ++j) sum += (double)__uint_as_float(s[j]);
+  // exclusive scan of the 1024 chunk sums
+  double incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    double w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;  // exclusive
+  }
+  __syncthreads();
+  double cum = warp_tot[wid] + (incl - sum);
+  double bv = __longlong_as_double(0x7ff0000000000000ll);
+  int bi = 0x7fffffff;
+  for (int j = j0; j < j1; ++j) {
+    cum += (double)__uint_as_float(s[j]);
+    if (j < min_el) continue;
+    const double id = (double)(j + 1);
+    const double deno = pow(id / (double)n, lambda);
+    const double inv = 1.0 / deno;
+    const double frms = inv * inv * (1.0 / id) * cum;
+    if (frms < bv) { bv = frms; bi = j; }
+  }
+  // first minimum over the block: smaller value, then lower index
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { best_v[wid] = bv; best_i[wid] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 32; ++w)
+      if (best_v[w] < bv || (best_v[w] == bv && best_i[w] < bi)) { bv = best_v[w]; bi = best_i[w]; }
+    if (bi == 0x7fffffff) bi = min_el;
+    const float ratio = __fdiv_rn((float)bi, (float)n);
+    const double q = (double)ratio;
+    unsigned long long rank = (q == 1.0) ? (unsigned long long)(M - 1) : (unsigned long long)((double)M * q);
+    if (rank >= (unsigned long long)M) rank = M - 1;
+    limit_out[blockIdx.x] = __uint_as_float(s[rank]);
+    fail_out[blockIdx.x] = 0;
+  }
+}
+
+// fold the VarTrimmed limit of quantile slot jq into the pair's limits (what the third
+// select pass does for a fixed ratio)
+__global__ void var_apply_kernel(PairState* __restrict__ states, IcpParams P, int jq, const float* __restrict__ limit,
+                                 const int* __restrict__ fail, int n_pairs, int* n_active, volatile int* h_done) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  PairState& st = states[p];
+  if (!st.active) return;
+  if (fail[p]) {  // "no outlier to filter"
+    st.status = PGS_CONVERGENCE_ERROR;
+    st.active = 0;
+    pair_finished(n_active, h_done);
+    return;
+  }
+  const float hi = jq == 0 ? P.fixed_hi : st.lim_hi;
+  st.lim_hi = fminf(hi, __fmul_rn(P.q_factor[jq], limit[p]));
+  st.lim_lo = P.fixed_lo;
+}
+
 // no quantile-based filter in the chain: the limits are the fixed ones
 __global__ void fixed_limits_kernel(PairState* __restrict__ states, IcpParams P, int n_pairs) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -988,11 +1120,18 @@ void outlier_limits_params(const std::vector<Module>& filters, IcpParams* p) {
       continue;
     }
     p->has_outliers = 1;
-    if (f.name == "TrimmedDistOutlierFilter" || f.name == "MedianDistOutlierFilter") {
+    if (f.name == "TrimmedDistOutlierFilter" || f.name == "MedianDistOutlierFilter" ||
+        f.name == "VarTrimmedDistOutlierFilter") {
       if (p->n_quant == kMaxQuant) throw Error(PGS_INVALID_PARAMETER, "too many quantile-based outlier filters");
-      const bool trimmed = f.name[0] == 'T';
+      const bool trimmed = f.name[0] == 'T', var = f.name[0] == 'V';
       p->q_ratio[p->n_quant] = trimmed ? f.real("ratio") : 0.5;
-      p->q_factor[p->n_quant] = trimmed ? 1.0f : (float)f.real("factor");
+      p->q_factor[p->n_quant] = (trimmed || var) ? 1.0f : (float)f.real("factor");
+      p->q_var[p->n_quant] = var ? 1 : 0;
+      if (var) {
+        p->q_min[p->n_quant] = (float)f.real("minRatio");
+        p->q_max[p->n_quant] = (float)f.real("maxRatio");
+        p->q_lambda[p->n_quant] = f.real("lambda");
+      }
       p->n_quant++;
     } else if (f.name == "MaxDistOutlierFilter") {
       float m = (float)f.real("maxDist");
@@ -1373,6 +1512,28 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   DBuf<PairView> d_views(ctx, P);
   ctx->upload_small(d_views.p, hv.data(), sizeof(PairView) * P);
 
+  // ---- VarTrimmedDist work space: sort buffers for the k x N distances of every pair --------
+  bool any_var = false;
+  for (int jq = 0; jq < prm.n_quant; ++jq) any_var = any_var || prm.q_var[jq];
+  const int var_stride = ceil_div(std::max(max_nm, 1), kSortChunk) * kSortChunk;
+  DBuf<uint32_t> var_ka, var_kb, var_va, var_vb;
+  DBuf<VarIn> d_var_in;
+  DBuf<int> d_var_n, var_fail;
+  DBuf<float> var_limit;
+  if (any_var) {
+    var_ka.reset(ctx, (size_t)P * var_stride); var_kb.reset(ctx, (size_t)P * var_stride);
+    var_va.reset(ctx, (size_t)P * var_stride); var_vb.reset(ctx, (size_t)P * var_stride);
+    std::vector<VarIn> vin(P);
+    std::vector<int> vn(P);
+    for (int p = 0; p < P; ++p) {
+      vin[p] = VarIn{hv[p].match_d2, hv[p].n_m, &d_states.p[p].active};
+      vn[p] = hv[p].n_m;
+    }
+    d_var_in.reset(ctx, P); d_var_n.reset(ctx, P); var_fail.reset(ctx, P); var_limit.reset(ctx, P);
+    ctx->upload_small(d_var_in.p, vin.data(), sizeof(VarIn) * P);
+    ctx->upload_small(d_var_n.p, vn.data(), sizeof(int) * P);
+  }
+
   // ---- the loop ------------------------------------------------------------------
   ctx->ensure_progress();
   DBuf<int> d_nactive(ctx, 1);
@@ -1406,13 +1567,26 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     if (knn == 1) match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
     else launch_match_k(knn, gm, s, d_views.p, d_states.p, prm.max_r2);
     mark();
-    for (int jq = 0; jq < prm.n_quant; ++jq)
+    for (int jq = 0; jq < prm.n_quant; ++jq) {
+      if (prm.q_var[jq]) {
+        var_keys_kernel<<<dim3(ceil_div(std::max(max_nm, 1), 256), P), 256, 0, s>>>(d_var_in.p, var_ka.p, var_va.p, var_stride);
+        const bool in_b = radix_sort_pairs<uint32_t>(ctx, var_ka.p, var_kb.p, var_va.p, var_vb.p, d_var_n.p, P,
+                                                     var_stride, max_nm, 32);
+        var_limit_kernel<<<P, 1024, 0, s>>>(d_var_in.p, in_b ? var_kb.p : var_ka.p, var_stride, prm.q_min[jq],
+                                            prm.q_max[jq], prm.q_lambda[jq], var_limit.p, var_fail.p);
+        var_apply_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, jq, var_limit.p, var_fail.p, P, d_nactive.p,
+                                                        ctx->d_progress);
+        ctx_count_launches(ctx, 3);
+        continue;
+      }
       for (int pass = 0; pass < 3; ++pass)
         select_pass_kernel<<<gs, 256, 0, s>>>(d_views.p, d_states.p, prm, jq, pass, d_nactive.p, ctx->d_progress);
+    }
     mark();
     accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
     mark();
-    ctx_count_launches(ctx, 2 + 3 * prm.n_quant);
+    for (int jq = 0; jq < prm.n_quant; ++jq) ctx_count_launches(ctx, prm.q_var[jq] ? 0 : 3);
+    ctx_count_launches(ctx, 2);
     PGS_CUDA(cudaEventRecord(ctx->loop_ev[it & 1], s));
     ++launched;
   }
@@ -1503,6 +1677,28 @@ void outlier_weights_device(Ctx* ctx, const std::vector<Module>& filters, const 
     DBuf<float> q(ctx, kMaxQuant);
     DBuf<int> fail(ctx, kMaxQuant);
     for (int j = 0; j < p.n_quant; ++j) {
+      if (p.q_var[j]) {
+        if (nk > 0x7fffffff) throw Error(PGS_INVALID_PARAMETER, "VarTrimmedDistOutlierFilter: too many matches");
+        const int n = (int)nk;
+        const int stride = ceil_div(std::max(n, 1), kSortChunk) * kSortChunk;
+        DBuf<uint32_t> ka(ctx, stride), kb(ctx, stride), va(ctx, stride), vb(ctx, stride);
+        DBuf<VarIn> din(ctx, 1);
+        DBuf<int> dn(ctx, 1);
+        VarIn vin{d_d2, n, nullptr};
+        ctx->upload_small(din.p, &vin, sizeof(vin));
+        ctx->upload_small(dn.p, &n, sizeof(int));
+        if (n > 0) {
+          var_keys_kernel<<<dim3(ceil_div(n, 256), 1), 256, 0, ctx->stream>>>(din.p, ka.p, va.p, stride);
+          const bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, dn.p, 1, stride, n, 32);
+          var_limit_kernel<<<1, 1024, 0, ctx->stream>>>(din.p, in_b ? kb.p : ka.p, stride, p.q_min[j], p.q_max[j],
+                                                        p.q_lambda[j], q.p + j, fail.p + j);
+          ctx_count_launches(ctx, 2);
+        } else {
+          int one = 1;
+          ctx->upload_small(fail.p + j, &one, sizeof(int));
+        }
+        continue;
+      }
       quantile_kernel<<<1, 1024, 0, ctx->stream>>>(d_d2, nk, p.q_ratio[j], q.p + j, fail.p + j);
       ctx_count_launches(ctx, 1);
     }

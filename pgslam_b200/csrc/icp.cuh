@@ -33,6 +33,9 @@ struct IcpParams {
   int n_quant;         // quantile-based limits: hi = min_j factor_j * quantile(ratio_j)
   double q_ratio[kMaxQuant];
   float q_factor[kMaxQuant];
+  int q_var[kMaxQuant];      // 1: VarTrimmedDist (ratio optimised per iteration), else fixed ratio
+  float q_min[kMaxQuant], q_max[kMaxQuant];  // VarTrimmedDist minRatio / maxRatio
+  double q_lambda[kMaxQuant];
   float fixed_hi, fixed_lo;  // MaxDist^2 / MinDist^2 limits
   float max_r2;        // matcher maxDist^2
   int hard_iteration_cap;

@@ -83,6 +83,10 @@ const std::vector<ModuleDoc>& registry() {
       {Kind::OutlierFilter, "MaxDistOutlierFilter", {{"maxDist", "", "1", "0.0000001", INF, 'f'}}},
       {Kind::OutlierFilter, "MinDistOutlierFilter", {{"minDist", "", "1", "0.0000001", INF, 'f'}}},
       {Kind::OutlierFilter, "MedianDistOutlierFilter", {{"factor", "", "3", "0.0000001", INF, 'f'}}},
+      {Kind::OutlierFilter, "VarTrimmedDistOutlierFilter",
+       {{"minRatio", "lower bound of the optimised inlier ratio", "0.05", "0.0000001", "1", 'f'},
+        {"maxRatio", "upper bound of the optimised inlier ratio", "0.99", "0.0000001", "1", 'f'},
+        {"lambda", "exponent of the FRMS criterion", "0.95", "", "", 'f'}}},
       {Kind::OutlierFilter, "SurfaceNormalOutlierFilter",
        {{"maxAngle", "max angle (rad) between the normals of a matched pair", "1.57", "0.0", "3.1416", 'f'}}},
       // ---- ErrorMinimizers (A12, A12d, A13) ------------------------------

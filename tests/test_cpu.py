@@ -207,6 +207,34 @@ def test_oracle_quantile_is_the_exact_order_statistic():
     assert st == ob.CONVERGENCE_ERROR
 
 
+def test_oracle_var_trimmed_ratio_minimises_frms():
+    """VarTrimmedDistOutlierFilter: the oracle's optimised ratio against a direct numpy
+    evaluation of the FRMS criterion on the sorted valid distances."""
+    import ctypes as C
+    g = np.random.default_rng(5)
+    d = np.concatenate([g.gamma(2.0, 0.002, 4000), g.uniform(0.5, 4.0, 600)]).astype(np.float32)  # inliers + outliers
+    g.shuffle(d)
+    d[:7] = 0.0
+    d[7:12] = np.inf
+    for lo, hi, lam in ((0.05, 0.99, 0.95), (0.3, 0.8, 2.0), (0.5, 1.0, 0.5)):
+        ratio = C.c_float(0)
+        assert ob.lib().orc_var_trimmed_ratio(ob._f(d), d.size, lo, hi, lam, C.byref(ratio)) == 0
+        v = np.sort(d[np.isfinite(d) & (d > 0)]).astype(np.float64)
+        n = d.size
+        min_el, max_el = int(np.floor(np.float32(lo) * np.float32(n))), min(int(np.floor(np.float32(hi) * np.float32(n))), v.size)
+        ids = np.arange(min_el + 1, max_el + 1, dtype=np.float64)
+        frms = (1.0 / (ids / n) ** lam) ** 2 / ids * np.cumsum(v)[min_el:max_el]
+        want = np.float32(min_el + int(np.argmin(frms))) / np.float32(n)
+        assert ratio.value == want
+        # the outlier cluster (the last 13 %) is cut off whenever the range allows it
+        if lo < 0.5:
+            assert ratio.value < 4000 / 4600 + 0.01
+    st, w = ob.outlier_weights(["VarTrimmedDistOutlierFilter"], d[None, :])
+    assert st == 0 and w[0, 7:12].sum() == 0 and w[0, :7].sum() == 7  # inf -> 0, exact hits -> 1
+    st, _ = ob.outlier_weights(["VarTrimmedDistOutlierFilter"], np.zeros((1, 10), np.float32))
+    assert st == ob.CONVERGENCE_ERROR
+
+
 def test_oracle_dense_algebra_against_numpy():
     import ctypes as C
     L = ob.lib()

@@ -244,6 +244,37 @@ def test_outlier_weights_bit_exact(pm, pair30k, filters):
     assert np.array_equal(got, want)
 
 
+def test_var_trimmed_dist_outlier_filter(pm, pair30k):
+    rd, rf, _ = pair30k
+    ids, d2 = ob.kdtree_knn(rf, rd, k=2)
+    d2[0, :50] = 0.0       # exact hits and unfound matches are not "valid" distances
+    d2[1, 100:130] = np.inf
+    for params in ({}, {"minRatio": 0.3, "maxRatio": 0.9, "lambda": 2.0}):
+        filt = [{"VarTrimmedDistOutlierFilter": params}]
+        st, want = ob.outlier_weights(filt, d2)
+        assert st == 0
+        o = pm.OutlierFilters()
+        o.append("VarTrimmedDistOutlierFilter", params)
+        got = o.compute(pm.DataPoints(rd), pm.DataPoints(rf), pm.Matches(ids, d2))
+        assert np.array_equal(got, want)
+        assert 0.04 < want.mean() < 1.0
+    # fused loop: the ratio is re-optimised every iteration
+    cfg = dict(util.C2, outlierFilters=[{"VarTrimmedDistOutlierFilter": {"minRatio": 0.4, "maxRatio": 0.95}}])
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["weighted_point_used_ratio"] == pytest.approx(want["weighted_ratio"], rel=1e-12)
+    # combined with a fixed limit, and on a batch with a pair that has nothing to filter
+    cfg2 = dict(util.C1, outlierFilters=[{"MaxDistOutlierFilter": {"maxDist": 1.0}}, "VarTrimmedDistOutlierFilter"])
+    icp, T, want = _run_both(pm, cfg2, rd, rf)
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rf), pm.DataPoints(rf))  # every distance is 0
+    assert ob.icp_run(cfg2, ob.Cloud(rf), ob.Cloud(rf))["status"] == ob.CONVERGENCE_ERROR
+
+
 def test_outlier_no_valid_distance_is_convergence_error(pm):
     q = np.ones((4, 10), np.float32)
     d2 = np.zeros((1, 10), np.float32)
