@@ -19,7 +19,7 @@ OK, CONVERGENCE_ERROR, TRANSFORMATION_ERROR, INVALID_PARAMETER, INVALID_FIELD = 
 
 F_RANDOM_SAMPLING, F_VOXEL_GRID, F_SURFACE_NORMAL, F_OBSERVATION_DIRECTION = 1, 2, 3, 4
 F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST, F_BOUNDING_BOX = 5, 6, 7, 8, 9
-F_MAX_DENSITY = 10
+F_MAX_DENSITY, F_SAMPLING_SURFACE_NORMAL = 10, 11
 O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST, O_SURFACE_NORMAL = 1, 2, 3, 4, 5
 O_VAR_TRIMMED_DIST = 6
 E_POINT_TO_PLANE, E_POINT_TO_PLANE_WITH_COV, E_POINT_TO_POINT = 1, 2, 3
@@ -276,6 +276,13 @@ def make_filter(name: str, **p) -> CFilter:
         f.type, f.i0, f.p0 = F_MAX_DIST, int(p.get("dim", -1)), float(p.get("maxDist", 1.0))
     elif name == "MinDistDataPointsFilter":
         f.type, f.i0, f.p0 = F_MIN_DIST, int(p.get("dim", -1)), float(p.get("minDist", 1.0))
+    elif name == "SamplingSurfaceNormalDataPointsFilter":
+        f.type = F_SAMPLING_SURFACE_NORMAL
+        f.p0, f.p1, f.p2 = float(p.get("ratio", 0.5)), float(p.get("maxBoxDim", np.inf)), float(p.get("seed", 0))
+        f.i0 = int(p.get("knn", 7))
+        f.i1 = (int(p.get("keepNormals", 1)) | int(p.get("keepDensities", 0)) << 1 |
+                int(p.get("keepEigenValues", 0)) << 2 | int(p.get("keepEigenVectors", 0)) << 3 |
+                int(p.get("samplingMethod", 0)) << 4 | int(p.get("averageExistingDescriptors", 1)) << 5)
     elif name == "MaxDensityDataPointsFilter":
         f.type, f.p0, f.i0 = F_MAX_DENSITY, float(p.get("maxDensity", 10.0)), int(p.get("seed", 0))
     elif name == "BoundingBoxDataPointsFilter":
@@ -329,6 +336,13 @@ def _modlist(items):
         else:
             out.append((it[0], it[1] or {}))
     return out
+
+
+def default_config() -> CIcpConfig:
+    """ICPChainBase::setDefault."""
+    c = CIcpConfig()
+    lib().orc_icp_config_default(C.byref(c))
+    return c
 
 
 def config_from_dict(cfg: dict) -> CIcpConfig:

@@ -977,8 +977,193 @@ static int filter_max_density(const orc_filter *f, orc_cloud *c) {
   return ORC_OK;
 }
 
+/* SamplingSurfaceNormalDataPointsFilter [UPSTREAM-RECALLED,
+ * DataPointsFilters/SamplingSurfaceNormal.cpp buildNew / fuseRange]:
+ * the cloud is split recursively -- cut dimension = widest side of the INHERITED
+ * box, left half = count - count/2 smallest points along it, the inherited box
+ * is clipped at the first point of the right half -- until a cell holds at most
+ * knn points; every cell gets ONE normal (smallest eigenvector of its scatter
+ * matrix NN NN^T, not divided by the count) and is then subsampled: method 0
+ * keeps each point with probability `ratio`, method 1 keeps one point placed at
+ * the cell mean.  Cells wider than maxBoxDim or of rank < 2 are dropped.
+ * Pinned here where upstream leaves it to std::nth_element / rand(): the
+ * partition is the STABLE order by (coordinate, previous order) with floats
+ * compared through their total order (-0 < +0); the uniform variate of point k
+ * is the counter hash (H7); mean and scatter are fp64 (H4).                  */
+typedef struct { uint32_t key; int32_t ord; int32_t id; } ssn_item;
+static int cmp_ssn(const void *a, const void *b) {
+  const ssn_item *x = (const ssn_item *)a, *y = (const ssn_item *)b;
+  if (x->key != y->key) return x->key < y->key ? -1 : 1;
+  return x->ord < y->ord ? -1 : (x->ord > y->ord ? 1 : 0);
+}
+static inline uint32_t ord_u32(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+typedef struct {
+  const orc_filter *f;
+  orc_cloud *c;
+  int32_t *idx;
+  ssn_item *scratch;
+  uint8_t *keep;
+} ssn_ctx;
+
+static void ssn_fuse(ssn_ctx *s, int64_t first, int64_t last) {
+  orc_cloud *c = s->c;
+  const int flags = (int)s->f->i1;
+  const int cnt = (int)(last - first);
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  double mean[3] = {0, 0, 0};
+  for (int j = 0; j < cnt; ++j) {
+    const float *p = c->feat + 4 * (int64_t)s->idx[first + j];
+    for (int d = 0; d < 3; ++d) {
+      if (j == 0 || p[d] < lo[d]) lo[d] = p[d];
+      if (j == 0 || p[d] > hi[d]) hi[d] = p[d];
+      mean[d] += (double)p[d];
+    }
+  }
+  float box_dim = hi[0] - lo[0];
+  if (hi[1] - lo[1] > box_dim) box_dim = hi[1] - lo[1];
+  if (hi[2] - lo[2] > box_dim) box_dim = hi[2] - lo[2];
+  if (box_dim > (float)s->f->p1) return; /* drop box if it is too large */
+  for (int d = 0; d < 3; ++d) mean[d] = mean[d] / (double)cnt;
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, maxr2 = 0.0;
+  for (int j = 0; j < cnt; ++j) {
+    const float *p = c->feat + 4 * (int64_t)s->idx[first + j];
+    double dx = (double)p[0] - mean[0], dy = (double)p[1] - mean[1], dz = (double)p[2] - mean[2];
+    C[0] += dx * dx; C[1] += dx * dy; C[2] += dx * dz;
+    C[4] += dy * dy; C[5] += dy * dz; C[8] += dz * dz;
+    double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 > maxr2) maxr2 = r2;
+  }
+  C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  double w[3] = {1.0, 0.0, 0.0}, V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (flags & (1 | 4 | 8)) {
+    orc_eig3_sym(C, w, V);
+    double wmax = w[0] > w[1] ? w[0] : w[1];
+    if (w[2] > wmax) wmax = w[2];
+    int rank = 0;
+    for (int e = 0; e < 3; ++e)
+      if (w[e] > 3.0 * (double)FLT_EPSILON * wmax) ++rank;
+    if (rank < 2) return; /* degenerate cell */
+  }
+  float normal[3] = {0, 0, 0};
+  if (flags & 1) {
+    int e0 = 0;
+    for (int e = 1; e < 3; ++e)
+      if (w[e] < w[e0]) e0 = e;
+    for (int d = 0; d < 3; ++d) {
+      float v = (float)V[e0 * 3 + d];
+      normal[d] = v < -1.f ? -1.f : (v > 1.f ? 1.f : v);
+    }
+  }
+  float density = 0.f;
+  if (flags & 2) {
+    double r = sqrt(maxr2);
+    density = (float)((double)cnt / ((4.0 / 3.0) * 3.14159265358979323846 * (r * r * r)));
+  }
+#define SSN_WRITE(k)                                                            \
+  do {                                                                          \
+    if (flags & 1) for (int d = 0; d < 3; ++d) c->normals[3 * (k) + d] = normal[d]; \
+    if (flags & 2) c->dens[(k)] = density;                                       \
+    if (flags & 4) for (int e = 0; e < 3; ++e) c->eigval[3 * (k) + e] = (float)w[e]; \
+    if (flags & 8) for (int e = 0; e < 9; ++e) c->eigvec[9 * (k) + e] = (float)V[e]; \
+  } while (0)
+  if (!(flags & 16)) {
+    for (int j = 0; j < cnt; ++j) {
+      int64_t k = s->idx[first + j];
+      if (hash_uniform((uint64_t)s->f->p2, (uint64_t)k) < (float)s->f->p0) {
+        s->keep[k] = 1;
+        SSN_WRITE(k);
+      }
+    }
+  } else {
+    int64_t k = s->idx[first];
+    s->keep[k] = 1;
+    if (flags & 32) {
+      /* average the existing descriptors over the cell, in cell order, in T */
+#define SSN_AVG(field, span)                                                    \
+      if (c->field) {                                                            \
+        for (int d = 0; d < (span); ++d) {                                       \
+          float acc = 0.f;                                                       \
+          for (int j = 0; j < cnt; ++j) acc = acc + c->field[(size_t)s->idx[first + j] * (span) + d]; \
+          c->field[(size_t)k * (span) + d] = acc / (float)cnt;                   \
+        }                                                                        \
+      }
+      SSN_AVG(normals, 3) SSN_AVG(obsdir, 3) SSN_AVG(noise, 1) SSN_AVG(dens, 1) SSN_AVG(eigval, 3)
+      SSN_AVG(eigvec, 9) SSN_AVG(meandist, 1) SSN_AVG(matched, c->matched_span)
+#undef SSN_AVG
+    }
+    for (int d = 0; d < 3; ++d) c->feat[4 * k + d] = (float)mean[d];
+    c->feat[4 * k + 3] = 1.f;
+    SSN_WRITE(k);
+  }
+#undef SSN_WRITE
+}
+
+static void ssn_build(ssn_ctx *s, int64_t first, int64_t last, const float *minv, const float *maxv) {
+  const int64_t count = last - first;
+  if (count <= s->f->i0) {
+    if (count > 0) ssn_fuse(s, first, last);
+    return;
+  }
+  int cut = 0;
+  for (int d = 1; d < 3; ++d)
+    if (maxv[d] - minv[d] > maxv[cut] - minv[cut]) cut = d;
+  const int64_t right = count / 2, left = count - right;
+  for (int64_t j = 0; j < count; ++j) {
+    s->scratch[j].key = ord_u32(s->c->feat[4 * (int64_t)s->idx[first + j] + cut]);
+    s->scratch[j].ord = (int32_t)j;
+    s->scratch[j].id = s->idx[first + j];
+  }
+  qsort(s->scratch, (size_t)count, sizeof(ssn_item), cmp_ssn);
+  for (int64_t j = 0; j < count; ++j) s->idx[first + j] = s->scratch[j].id;
+  const float cut_val = s->c->feat[4 * (int64_t)s->idx[first + left] + cut];
+  float lmax[3] = {maxv[0], maxv[1], maxv[2]}, rmin[3] = {minv[0], minv[1], minv[2]};
+  lmax[cut] = cut_val;
+  rmin[cut] = cut_val;
+  ssn_build(s, first, first + left, minv, lmax);
+  ssn_build(s, first + left, last, rmin, maxv);
+}
+
+static int filter_sampling_surface_normal(const orc_filter *f, orc_cloud *c) {
+  const int64_t n = c->n;
+  const int flags = (int)f->i1;
+  if (f->i0 < 3) return ORC_INVALID_PARAMETER;
+  if ((flags & 1) && !c->normals) c->normals = (float *)calloc((size_t)(n + 1) * 3, sizeof(float));
+  if ((flags & 2) && !c->dens) c->dens = (float *)calloc((size_t)(n + 1), sizeof(float));
+  if ((flags & 4) && !c->eigval) c->eigval = (float *)calloc((size_t)(n + 1) * 3, sizeof(float));
+  if ((flags & 8) && !c->eigvec) c->eigvec = (float *)calloc((size_t)(n + 1) * 9, sizeof(float));
+  ssn_ctx s;
+  s.f = f;
+  s.c = c;
+  s.idx = (int32_t *)malloc((size_t)(n + 1) * sizeof(int32_t));
+  s.scratch = (ssn_item *)malloc((size_t)(n + 1) * sizeof(ssn_item));
+  s.keep = (uint8_t *)calloc((size_t)(n + 1), 1);
+  float minv[3] = {0, 0, 0}, maxv[3] = {0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    s.idx[i] = (int32_t)i;
+    for (int d = 0; d < 3; ++d) {
+      float v = c->feat[4 * i + d];
+      if (i == 0 || v < minv[d]) minv[d] = v;
+      if (i == 0 || v > maxv[d]) maxv[d] = v;
+    }
+  }
+  ssn_build(&s, 0, n, minv, maxv);
+  int64_t *sel = (int64_t *)malloc((size_t)(n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (s.keep[i]) sel[m++] = i;
+  cloud_select(c, sel, m);
+  free(sel); free(s.idx); free(s.scratch); free(s.keep);
+  return ORC_OK;
+}
+
 int orc_filter_apply(const orc_filter *f, orc_cloud *c) {
   switch (f->type) {
+    case ORC_F_SAMPLING_SURFACE_NORMAL: return filter_sampling_surface_normal(f, c);
     case ORC_F_MAX_DENSITY: return filter_max_density(f, c);
     case ORC_F_BOUNDING_BOX: return filter_bounding_box(f, c);
     case ORC_F_RANDOM_SAMPLING: return filter_random_sampling(f, c);
@@ -1579,9 +1764,19 @@ static int chk_check(checkers *c, const double *T, int *iterate, int *max_reache
 /* ICP chain (§3.3, A.8)                                                    */
 /* ======================================================================== */
 void orc_icp_config_default(orc_icp_config *cfg) {
-  /* ICPChainBase::setDefault with the SamplingSurfaceNormal reference filter
-   * replaced by SurfaceNormal(knn) as pgslam-style YAMLs do (A17)          */
+  /* ICPChainBase::setDefault (A17): RandomSampling(0.75) reading filter,
+   * SamplingSurfaceNormal reference filter, TrimmedDist(0.85), k = 1,
+   * PointToPlane, Counter(40) + Differential(0.001, 0.001, 3)              */
   memset(cfg, 0, sizeof(*cfg));
+  cfg->reading_filters[0].type = ORC_F_RANDOM_SAMPLING;
+  cfg->reading_filters[0].p0 = 0.75;
+  cfg->n_reading_filters = 1;
+  cfg->reference_filters[0].type = ORC_F_SAMPLING_SURFACE_NORMAL;
+  cfg->reference_filters[0].p0 = 0.5;
+  cfg->reference_filters[0].p1 = INFINITY;
+  cfg->reference_filters[0].i0 = 7;
+  cfg->reference_filters[0].i1 = 1 | 32;
+  cfg->n_reference_filters = 1;
   cfg->knn = 1;
   cfg->epsilon = 0.0;
   cfg->max_dist = INFINITY;

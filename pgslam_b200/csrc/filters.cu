@@ -476,6 +476,286 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   PGS_LAUNCH_CHECK();
 }
 
+// ---------------------------------------------------------------------------
+// SamplingSurfaceNormalDataPointsFilter: recursive median cells of at most knn
+// points, one normal per cell, subsampled.  The recursion is level-synchronous:
+// the cell COUNTS depend only on n (left = count - count/2), so the host lays
+// out every level's cells; the device orders the points of all splitting cells
+// of a level with one stable radix sort keyed (cell, coordinate along the cell's
+// cut dimension) and clips the inherited boxes at the cut values.
+// ---------------------------------------------------------------------------
+struct SsnCell {
+  int first, count;
+  int parent;  // cell of the previous level this one came from
+  int side;    // 0: unsplit copy of the parent, 1: left half, 2: right half
+};
+
+__global__ void __launch_bounds__(256)
+ssn_cut_kernel(const float* __restrict__ box, const SsnCell* __restrict__ cells, int n_cells, int knn, int* __restrict__ cut) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_cells) return;
+  if (cells[s].count <= knn) { cut[s] = -1; return; }
+  const float* b = box + 6 * (size_t)s;
+  int c = 0;
+  for (int d = 1; d < 3; ++d)
+    if (__fsub_rn(b[3 + d], b[d]) > __fsub_rn(b[3 + c], b[c])) c = d;
+  cut[s] = c;
+}
+
+__global__ void __launch_bounds__(256)
+ssn_key_kernel(const float4* __restrict__ feat, const uint32_t* __restrict__ order, int n, const SsnCell* __restrict__ cells,
+               int n_cells, const int* __restrict__ cut, uint64_t* __restrict__ keys) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int lo = 0, hi = n_cells;  // last cell with first <= j
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cells[mid].first <= j) lo = mid; else hi = mid;
+  }
+  const int c = cut[lo];
+  uint32_t low;
+  if (c < 0) {
+    low = (uint32_t)(j - cells[lo].first);  // a finished cell keeps its order
+  } else {
+    const float4 p = feat[order[j]];
+    low = f2ord(c == 0 ? p.x : (c == 1 ? p.y : p.z));
+  }
+  keys[j] = ((uint64_t)lo << 32) | low;
+}
+
+// boxes of the next level's cells: the parent's inherited box, clipped at the cut value
+// (the coordinate of the first point of the right half) along the parent's cut dimension
+__global__ void __launch_bounds__(256)
+ssn_child_box_kernel(const float4* __restrict__ feat, const uint32_t* __restrict__ order, const SsnCell* __restrict__ parents,
+                     const int* __restrict__ cut, const float* __restrict__ box_in, const SsnCell* __restrict__ cells,
+                     int n_cells, float* __restrict__ box_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_cells) return;
+  const SsnCell me = cells[s];
+  float b[6];
+  for (int d = 0; d < 6; ++d) b[d] = box_in[6 * (size_t)me.parent + d];
+  if (me.side != 0) {
+    const SsnCell par = parents[me.parent];
+    const int c = cut[me.parent];
+    const int left = par.count - par.count / 2;
+    const float4 p = feat[order[par.first + left]];
+    const float v = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    if (me.side == 1) b[3 + c] = v; else b[c] = v;
+  }
+  for (int d = 0; d < 6; ++d) box_out[6 * (size_t)s + d] = b[d];
+}
+
+struct SsnOut {
+  float* normals;
+  float* dens;
+  float* eigval;
+  float* eigvec;
+};
+
+__global__ void __launch_bounds__(128)
+ssn_fuse_kernel(float4* __restrict__ feat, const uint32_t* __restrict__ order, const SsnCell* __restrict__ cells, int n_cells,
+                SsnOut out, DescList avg, int bin_method, float ratio, float max_box_dim, uint64_t seed, int need_eigen,
+                int* __restrict__ keep) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_cells) return;
+  const int first = cells[s].first, cnt = cells[s].count;
+  if (cnt <= 0) return;
+  float lo[3], hi[3];
+  double mean[3] = {0.0, 0.0, 0.0};
+  for (int j = 0; j < cnt; ++j) {
+    const float4 p4 = feat[order[first + j]];
+    const float p[3] = {p4.x, p4.y, p4.z};
+    for (int d = 0; d < 3; ++d) {
+      if (j == 0 || p[d] < lo[d]) lo[d] = p[d];
+      if (j == 0 || p[d] > hi[d]) hi[d] = p[d];
+      mean[d] += (double)p[d];
+    }
+  }
+  float box_dim = __fsub_rn(hi[0], lo[0]);
+  if (__fsub_rn(hi[1], lo[1]) > box_dim) box_dim = __fsub_rn(hi[1], lo[1]);
+  if (__fsub_rn(hi[2], lo[2]) > box_dim) box_dim = __fsub_rn(hi[2], lo[2]);
+  if (box_dim > max_box_dim) return;
+  for (int d = 0; d < 3; ++d) mean[d] = mean[d] / (double)cnt;
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, maxr2 = 0.0;
+  for (int j = 0; j < cnt; ++j) {
+    const float4 p = feat[order[first + j]];
+    const double dx = (double)p.x - mean[0], dy = (double)p.y - mean[1], dz = (double)p.z - mean[2];
+    C[0] += dx * dx; C[1] += dx * dy; C[2] += dx * dz;
+    C[4] += dy * dy; C[5] += dy * dz; C[8] += dz * dz;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 > maxr2) maxr2 = r2;
+  }
+  C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  double w[3] = {1.0, 0.0, 0.0}, V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (need_eigen) {
+    jacobi_sym<3>(C, w, V);
+    double wmax = w[0] > w[1] ? w[0] : w[1];
+    if (w[2] > wmax) wmax = w[2];
+    int rank = 0;
+    for (int e = 0; e < 3; ++e)
+      if (w[e] > 3.0 * 1.1920928955078125e-07 * wmax) ++rank;
+    if (rank < 2) return;
+  }
+  float normal[3] = {0.f, 0.f, 0.f};
+  if (out.normals) {
+    int e0 = 0;
+    for (int e = 1; e < 3; ++e)
+      if (w[e] < w[e0]) e0 = e;
+    for (int d = 0; d < 3; ++d) {
+      const float v = (float)V[e0 * 3 + d];
+      normal[d] = v < -1.f ? -1.f : (v > 1.f ? 1.f : v);
+    }
+  }
+  float density = 0.f;
+  if (out.dens) {
+    const double r = sqrt(maxr2);
+    density = (float)((double)cnt / ((4.0 / 3.0) * 3.14159265358979323846 * (r * r * r)));
+  }
+  auto write = [&](int k) {
+    if (out.normals) for (int d = 0; d < 3; ++d) out.normals[3 * (size_t)k + d] = normal[d];
+    if (out.dens) out.dens[k] = density;
+    if (out.eigval) for (int e = 0; e < 3; ++e) out.eigval[3 * (size_t)k + e] = (float)w[e];
+    if (out.eigvec) for (int e = 0; e < 9; ++e) out.eigvec[9 * (size_t)k + e] = (float)V[e];
+  };
+  if (!bin_method) {
+    for (int j = 0; j < cnt; ++j) {
+      const int k = (int)order[first + j];
+      const uint64_t h = splitmix64(splitmix64(seed) ^ ((uint64_t)k * 0xD1B54A32D192ED03ull));
+      const float r = __fmul_rn((float)(h >> 40), 1.0f / 16777216.0f);
+      if (r < ratio) { keep[k] = 1; write(k); }
+    }
+  } else {
+    const int k = (int)order[first];
+    keep[k] = 1;
+    for (int q = 0; q < avg.count; ++q) {
+      float* D = avg.d[q].data;
+      const int span = avg.d[q].span;
+      for (int d = 0; d < span; ++d) {
+        float acc = 0.f;
+        for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, D[(size_t)order[first + j] * span + d]);
+        D[(size_t)k * span + d] = __fdiv_rn(acc, (float)cnt);
+      }
+    }
+    feat[k] = make_float4((float)mean[0], (float)mean[1], (float)mean[2], 1.f);
+    write(k);
+  }
+}
+
+__global__ void ssn_iota_kernel(uint32_t* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+void sampling_surface_normals(Ctx* ctx, const Module& m, Cloud& c) {
+  const int n = (int)c.n;
+  if (n == 0) return;
+  cudaStream_t s = ctx->stream;
+  const int knn = (int)m.integer("knn");
+  const bool bin = m.integer("samplingMethod") == 1;
+  // ---- the cell layout of every level (depends on n and knn only) ------------------
+  std::vector<std::vector<SsnCell>> levels;
+  levels.push_back({SsnCell{0, n, 0, 0}});
+  while (true) {
+    const auto& cur = levels.back();
+    bool any = false;
+    std::vector<SsnCell> next;
+    next.reserve(cur.size() * 2);
+    for (int i = 0; i < (int)cur.size(); ++i) {
+      if (cur[i].count > knn) {
+        const int right = cur[i].count / 2, left = cur[i].count - right;
+        next.push_back(SsnCell{cur[i].first, left, i, 1});
+        next.push_back(SsnCell{cur[i].first + left, right, i, 2});
+        any = true;
+      } else {
+        next.push_back(SsnCell{cur[i].first, cur[i].count, i, 0});
+      }
+    }
+    if (!any) break;
+    levels.push_back(std::move(next));
+  }
+  size_t max_cells = 1;
+  for (auto& l : levels) max_cells = std::max(max_cells, l.size());
+  // ---- device state -------------------------------------------------------------------
+  const int stride = ceil_div(n, kSortChunk) * kSortChunk;
+  DBuf<uint64_t> ka(ctx, stride), kb(ctx, stride);
+  DBuf<uint32_t> va(ctx, stride), vb(ctx, stride);
+  DBuf<int> d_n(ctx, 1), cut(ctx, max_cells);
+  DBuf<SsnCell> cells_a(ctx, max_cells), cells_b(ctx, max_cells);
+  DBuf<float> box_a(ctx, 6 * max_cells), box_b(ctx, 6 * max_cells);
+  ctx->upload_small(d_n.p, &n, sizeof(int));
+  ssn_iota_kernel<<<ceil_div(n, 256), 256, 0, s>>>(va.p, n);
+  {
+    // the root's inherited box is the cloud's bounding box
+    DBuf<unsigned> bb(ctx, 6);
+    minmax_init_kernel<<<1, 32, 0, s>>>(bb.p);
+    minmax_kernel<<<std::min(ceil_div(n, 1024), 128), 256, 0, s>>>(c.feat.p, n, bb.p);
+    minmax_decode_kernel<<<1, 32, 0, s>>>(bb.p, box_a.p);
+    ctx_count_launches(ctx, 4);
+  }
+  uint32_t* order = va.p;
+  uint32_t* order_alt = vb.p;
+  SsnCell* cells = cells_a.p;
+  SsnCell* cells_next = cells_b.p;
+  float* box = box_a.p;
+  float* box_next = box_b.p;
+  auto upload_cells = [&](SsnCell* dst, const std::vector<SsnCell>& v) {
+    // level tables can exceed the small-upload ring: plain async copy from a staging vector that
+    // outlives the copy (synchronised below, once per level)
+    PGS_CUDA(cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(SsnCell), cudaMemcpyHostToDevice, s));
+  };
+  upload_cells(cells, levels[0]);
+  for (size_t l = 0; l + 1 < levels.size(); ++l) {
+    const int nc = (int)levels[l].size(), nn = (int)levels[l + 1].size();
+    ssn_cut_kernel<<<ceil_div(nc, 256), 256, 0, s>>>(box, cells, nc, knn, cut.p);
+    ssn_key_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, order, n, cells, nc, cut.p, ka.p);
+    ctx_count_launches(ctx, 2);
+    int bits = 32;
+    while ((1 << (bits - 32)) < nc) ++bits;
+    // vals travel with the keys: (ka, order) -> sorted
+    uint32_t* v_in = order;
+    uint32_t* v_out = order_alt;
+    const bool in_b = radix_sort_pairs<uint64_t>(ctx, ka.p, kb.p, v_in, v_out, d_n.p, 1, stride, n, bits);
+    if (in_b) std::swap(order, order_alt);
+    upload_cells(cells_next, levels[l + 1]);
+    ssn_child_box_kernel<<<ceil_div(nn, 256), 256, 0, s>>>(c.feat.p, order, cells, cut.p, box, cells_next, nn, box_next);
+    ctx_count_launches(ctx, 1);
+    std::swap(cells, cells_next);
+    std::swap(box, box_next);
+    ctx->sync();  // the pageable level table has been consumed
+  }
+  ctx->sync();
+  // ---- one normal per cell, subsampling ----------------------------------------------
+  c.touch();
+  SsnOut out{nullptr, nullptr, nullptr, nullptr};
+  if (m.flag("keepNormals")) c.add("normals", 3);
+  if (m.flag("keepDensities")) c.add("densities", 1);
+  if (m.flag("keepEigenValues")) c.add("eigValues", 3);
+  if (m.flag("keepEigenVectors")) c.add("eigVectors", 9);
+  if (m.flag("keepNormals")) out.normals = c.find("normals")->data.p;
+  if (m.flag("keepDensities")) out.dens = c.find("densities")->data.p;
+  if (m.flag("keepEigenValues")) out.eigval = c.find("eigValues")->data.p;
+  if (m.flag("keepEigenVectors")) out.eigvec = c.find("eigVectors")->data.p;
+  DescList avg;
+  avg.count = 0;
+  if (bin && m.flag("averageExistingDescriptors")) {
+    for (auto& d : c.descs) {
+      float* p = d.data.p;
+      if (p == out.normals || p == out.dens || p == out.eigval || p == out.eigvec) continue;  // overwritten below
+      if (avg.count == kMaxDesc) throw Error(PGS_INVALID_PARAMETER, "SamplingSurfaceNormalDataPointsFilter: too many descriptors");
+      avg.d[avg.count++] = DescPtr{p, d.span};
+    }
+  }
+  DBuf<int> keep(ctx, n);
+  keep.zero();
+  const int nc = (int)levels.back().size();
+  const int need_eigen = (out.normals || out.eigval || out.eigvec) ? 1 : 0;
+  ssn_fuse_kernel<<<ceil_div(nc, 128), 128, 0, s>>>(c.feat.p, order, cells, nc, out, avg, bin ? 1 : 0, (float)m.real("ratio"),
+                                                    (float)m.real("maxBoxDim"), (uint64_t)m.integer("seed"), need_eigen, keep.p);
+  ctx_count_launches(ctx, 1);
+  PGS_LAUNCH_CHECK();
+  compact_cloud(c, keep.p);
+}
+
 }  // namespace
 
 bool is_rigid(const double* T) {
@@ -512,6 +792,7 @@ void apply_filter(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
     Cloud& c = *cp;
     const int n = (int)c.n;
     if (name == "VoxelGridDataPointsFilter") { voxel_grid(ctx, m, c); continue; }
+    if (name == "SamplingSurfaceNormalDataPointsFilter") { sampling_surface_normals(ctx, m, c); continue; }
     if (name == "ObservationDirectionDataPointsFilter") {
       float* o = c.add("observationDirections", 3).data.p;
       if (n) obsdir_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, o, n, (float)m.real("x"), (float)m.real("y"), (float)m.real("z"));

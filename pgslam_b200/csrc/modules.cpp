@@ -62,6 +62,17 @@ const std::vector<ModuleDoc>& registry() {
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"maxDist", "", "1", NINF, INF, 'f'}}},
       {Kind::DataPointsFilter, "MinDistDataPointsFilter",
        {{"dim", "axis, -1 = radial", "-1", "-1", "2", 'i'}, {"minDist", "", "1", NINF, INF, 'f'}}},
+      {Kind::DataPointsFilter, "SamplingSurfaceNormalDataPointsFilter",
+       {{"ratio", "ratio of points to keep with random subsampling", "0.5", "0.0000001", "1.0", 'f'},
+        {"knn", "largest number of points in a cell", "7", "3", "64", 'i'},
+        {"samplingMethod", "0: keep points of a cell at random, 1: one point at the cell mean", "0", "0", "1", 'i'},
+        {"maxBoxDim", "cells wider than this are dropped", INF, "0", INF, 'f'},
+        {"averageExistingDescriptors", "average the descriptors of a cell (samplingMethod 1)", "1", "0", "1", 'u'},
+        {"keepNormals", "", "1", "0", "1", 'u'},
+        {"keepDensities", "", "0", "0", "1", 'u'},
+        {"keepEigenValues", "", "0", "0", "1", 'u'},
+        {"keepEigenVectors", "", "0", "0", "1", 'u'},
+        {"seed", "seed of the counter-based generator (SURVEY H7)", "0", "0", "", 'i'}}},
       {Kind::DataPointsFilter, "MaxDensityDataPointsFilter",
        {{"maxDensity", "points denser than this are subsampled towards it", "10", "0.0000001", INF, 'f'},
         {"seed", "seed of the counter-based generator (SURVEY H7)", "0", "0", "", 'i'}}},
@@ -464,11 +475,12 @@ std::vector<Module> module_list_from_yaml(Kind kind, const YamlNode& node) {
 }
 
 ChainConfig chain_default() {
-  // ICPChainBase::setDefault (A17).  SamplingSurfaceNormal is upstream's default
-  // reference filter; this library provides SurfaceNormal (knn 10) in its place.
+  // ICPChainBase::setDefault (A17): RandomSampling(0.75) on the reading,
+  // SamplingSurfaceNormal on the reference, TrimmedDist(0.85), KDTreeMatcher,
+  // PointToPlane, Counter + Differential checkers
   ChainConfig c;
   c.reading_filters.push_back(create_module(Kind::DataPointsFilter, "RandomSamplingDataPointsFilter", {}));
-  c.reference_filters.push_back(create_module(Kind::DataPointsFilter, "SurfaceNormalDataPointsFilter", {{"knn", "10"}}));
+  c.reference_filters.push_back(create_module(Kind::DataPointsFilter, "SamplingSurfaceNormalDataPointsFilter", {}));
   c.outlier_filters.push_back(create_module(Kind::OutlierFilter, "TrimmedDistOutlierFilter", {}));
   c.matcher = create_module(Kind::Matcher, "KDTreeMatcher", {});
   c.minimizer = create_module(Kind::ErrorMinimizer, "PointToPlaneErrorMinimizer", {});

@@ -369,6 +369,40 @@ def test_oracle_icp_with_knn_3_and_step_filters():
     assert np.abs(s1["T"][:3, 3] - truth[:3, 3]).max() < 0.05
 
 
+def test_oracle_sampling_surface_normal_cells():
+    """SamplingSurfaceNormal: cells of at most knn points whose sizes follow the
+    left = count - count/2 rule; one unit normal per cell; bin mode keeps one point per cell
+    at the cell mean; on a plane every normal is the plane normal."""
+    g = np.random.default_rng(11)
+    n, knn = 5000, 7
+    pts = np.ones((4, n), np.float32)
+    pts[0], pts[1] = g.uniform(-5, 5, n), g.uniform(-3, 3, n)
+    pts[2] = (0.2 * pts[0] - 0.1 * pts[1] + 1.0 + g.normal(0, 1e-4, n)).astype(np.float32)
+
+    def cells(c):
+        return 1 if c <= knn else cells(c - c // 2) + cells(c // 2)
+
+    b = ob.Cloud(pts)
+    assert ob.apply_filter(b, "SamplingSurfaceNormalDataPointsFilter", knn=knn, samplingMethod=1) == 0
+    assert b.n == cells(n)
+    nrm = b.desc("normals").astype(np.float64)
+    want = np.array([0.2, -0.1, -1.0]) / np.linalg.norm([0.2, -0.1, -1.0])
+    assert np.abs(np.abs(nrm.T @ want) - 1.0).max() < 2e-3  # 0.1 mm noise over ~0.2 m cells
+    # the kept points are cell means: they lie on the plane, inside the cloud's extent
+    m = b.features.astype(np.float64)
+    assert np.abs(0.2 * m[0] - 0.1 * m[1] + 1.0 - m[2]).max() < 1e-3
+    r = ob.Cloud(pts)
+    assert ob.apply_filter(r, "SamplingSurfaceNormalDataPointsFilter", knn=knn, ratio=0.5, seed=3) == 0
+    assert abs(r.n / n - 0.5) < 0.03
+    # random mode keeps original points, in their original order
+    f = r.features
+    pos = [np.flatnonzero((pts[:3].T == f[:3, j]).all(axis=1))[0] for j in range(0, r.n, 97)]
+    assert pos == sorted(pos)
+    # maxBoxDim below the cell size drops everything
+    d = ob.Cloud(pts)
+    assert ob.apply_filter(d, "SamplingSurfaceNormalDataPointsFilter", knn=knn, maxBoxDim=1e-3) == 0 and d.n == 0
+
+
 def test_oracle_surface_normal_optional_descriptors():
     """keepMatchedIds / keepMeanDist / sortEigen against numpy on the same neighbourhoods."""
     _, rf, _ = synth.scan_pair(23, beams=16, az_steps=120)

@@ -174,6 +174,56 @@ def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
     _cmp_cloud(dp, oc)
 
 
+@pytest.mark.parametrize("params", [
+    {},
+    {"knn": 12, "ratio": 0.3, "seed": 5, "keepDensities": 1, "keepEigenValues": 1, "keepEigenVectors": 1},
+    {"samplingMethod": 1, "knn": 9, "keepDensities": 1},
+    {"samplingMethod": 1, "averageExistingDescriptors": 0, "maxBoxDim": 0.6, "keepNormals": 0, "keepDensities": 1},
+])
+def test_sampling_surface_normal_filter_bit_exact(pm, pair30k, params):
+    rd, _, _ = pair30k
+    # existing descriptors travel with the kept points (and are averaged per cell in bin mode)
+    pre = ["ObservationDirectionDataPointsFilter", {"SimpleSensorNoiseDataPointsFilter": {"sensorType": 0}}]
+    chain = pre + [{"SamplingSurfaceNormalDataPointsFilter": params}]
+    dp = pm.DataPoints(rd)
+    pm.DataPointsFilters(util.to_yaml(chain)).apply(dp)
+    oc = ob.Cloud(rd)
+    for it in chain:
+        (name, p), = ob._modlist([it])
+        assert ob.apply_filter(oc, name, **p) == 0
+    assert 0 < oc.n < rd.shape[1]
+    _cmp_cloud(dp, oc)
+
+
+def test_sampling_surface_normal_small_and_ragged(pm):
+    g = np.random.default_rng(1)
+    for n in (1, 5, 7, 8, 15, 100, 1001):
+        pts = np.ones((4, n), np.float32)
+        pts[:3] = g.normal(size=(3, n)).astype(np.float32)
+        for params in ({"ratio": 1.0}, {"samplingMethod": 1}):
+            dp = pm.DataPoints(pts)
+            f = pm.DataPointsFilters()
+            f.append("SamplingSurfaceNormalDataPointsFilter", params)
+            f.apply(dp)
+            oc = ob.Cloud(pts)
+            assert ob.apply_filter(oc, "SamplingSurfaceNormalDataPointsFilter", **params) == 0
+            _cmp_cloud(dp, oc)
+
+
+def test_icp_default_chain_is_upstreams_set_default(pm, pair30k):
+    """ICP() without a YAML = ICPChainBase::setDefault: RandomSampling reading filter,
+    SamplingSurfaceNormal reference filter, TrimmedDist 0.85, point-to-plane."""
+    rd, rf, truth = pair30k
+    icp = pm.ICP()
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    want = ob.icp_run(ob.default_config(), ob.Cloud(rd), ob.Cloud(rf))
+    assert want["status"] == 0
+    assert icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    assert icp.last["n_reference"] < rf.shape[1] and icp.last["n_reading"] < rd.shape[1]
+    assert np.abs(T[:3, 3] - truth[:3, 3]).max() < 0.05
+
+
 def test_max_density_filter_bit_exact(pm, pair30k):
     rd, _, _ = pair30k
     chain = [{"SurfaceNormalDataPointsFilter": {"knn": 8, "keepDensities": 1}},
