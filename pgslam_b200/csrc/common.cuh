@@ -138,16 +138,66 @@ __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float px
   return d;
 }
 
-// lower bound of dist2_rn over an axis-aligned box, same operation order, so
-// by monotonicity of IEEE rounding it never exceeds the computed distance to
-// any point inside the box.
-__device__ __forceinline__ float box_lb_rn(float qx, float qy, float qz, float lx, float ly, float lz,
-                                           float hx, float hy, float hz) {
-  float dx = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.f);
-  float dy = fmaxf(fmaxf(__fsub_rn(ly, qy), __fsub_rn(qy, hy)), 0.f);
-  float dz = fmaxf(fmaxf(__fsub_rn(lz, qz), __fsub_rn(qz, hz)), 0.f);
-  float d = __fmul_rn(dx, dx);
-  d = __fadd_rn(d, __fmul_rn(dy, dy));
+// ---- packed fp32x2 arithmetic (sm_100a: FADD2 / FMUL2 issue two IEEE-rn fp32 operations
+// per slot; each half rounds exactly like the scalar instruction, so results are unchanged).
+// Only SUB and MUL are used packed: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into a
+// fused FFMA2 even under -fmad=false (measured: 19 % of a*a+b results differ), which would
+// break the no-FMA contract, so sums of products stay scalar.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// dist2_rn with the x,y halves packed: same operations, same order, 6 issue slots instead of 8
+__device__ __forceinline__ float dist2_rn_packed(unsigned long long qxy, float qz, float px, float py, float pz) {
+  const unsigned long long dxy = sub_f32x2(qxy, pack_f32x2(px, py));
+  const unsigned long long sq = mul_f32x2(dxy, dxy);
+  float sx, sy;
+  unpack_f32x2(sq, sx, sy);
+  const float dz = __fsub_rn(qz, pz);
+  float d = __fadd_rn(sx, sy);
+  d = __fadd_rn(d, __fmul_rn(dz, dz));
+  return d;
+}
+
+// Lower bound of dist2_rn over an axis-aligned box, same operation order, so by monotonicity
+// of IEEE rounding it never exceeds the computed distance to any point inside the box.
+// The node is stored {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z} (index.cu): the three
+// 8-byte halves arrive packed from the load, the six subtractions issue as three FADD2
+// (q.z - hi.z is taken as the exact negation of hi.z - q.z) and the x,y squares as one FMUL2.
+struct QueryPk {
+  unsigned long long xy, zz;
+  float z;
+};
+__device__ __forceinline__ QueryPk pack_query(float qx, float qy, float qz) {
+  return QueryPk{pack_f32x2(qx, qy), pack_f32x2(qz, qz), qz};
+}
+__device__ __forceinline__ float box_lb_packed(const QueryPk& q, unsigned long long lxy, unsigned long long hxy,
+                                               unsigned long long lhz) {
+  float ax, ay, bx, by, cl, ch;
+  unpack_f32x2(sub_f32x2(lxy, q.xy), ax, ay);
+  unpack_f32x2(sub_f32x2(q.xy, hxy), bx, by);
+  unpack_f32x2(sub_f32x2(lhz, q.zz), cl, ch);
+  const float dx = fmaxf(fmaxf(ax, bx), 0.f);
+  const float dy = fmaxf(fmaxf(ay, by), 0.f);
+  const float dz = fmaxf(fmaxf(cl, -ch), 0.f);
+  const unsigned long long dxy = pack_f32x2(dx, dy);
+  float sx, sy;
+  unpack_f32x2(mul_f32x2(dxy, dxy), sx, sy);
+  float d = __fadd_rn(sx, sy);
   d = __fadd_rn(d, __fmul_rn(dz, dz));
   return d;
 }

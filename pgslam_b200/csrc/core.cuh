@@ -94,7 +94,7 @@ static constexpr int kLeaf = 8;  // 8 float4 = one 128-byte line per leaf
 
 struct TreeView {
   const float4* pts;   // sorted; w = original index (int bits); padded to n_leaves*kLeaf
-  const float* nodes;  // 2*P nodes x {lo.xyz, hi.xyz}; node 0 unused
+  const float* nodes;  // 2*P nodes x {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z}; node 0 unused
   int n;
   int n_leaves;
   int P;      // leaves rounded up to a power of two

@@ -135,8 +135,10 @@ __global__ void __launch_bounds__(256) leaf_box_kernel(const BuildJob* __restric
     }
   }
   float* nd = job.nodes + (size_t)(job.P + leaf) * 6;
-  nd[0] = lo[0]; nd[1] = lo[1]; nd[2] = lo[2];
-  nd[3] = hi[0]; nd[4] = hi[1]; nd[5] = hi[2];
+  // node layout {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z}: three 8-byte halves that feed the
+  // packed fp32x2 box test (box_lb_packed) straight from the load
+  nd[0] = lo[0]; nd[1] = lo[1]; nd[2] = hi[0];
+  nd[3] = hi[1]; nd[4] = lo[2]; nd[5] = hi[2];
 }
 
 // one block per job walks the levels bottom-up
@@ -147,8 +149,8 @@ __global__ void __launch_bounds__(1024) upper_levels_kernel(const BuildJob* __re
       const int node = width + i;
       const float* a = job.nodes + (size_t)(2 * node) * 6;
       float* o = job.nodes + (size_t)node * 6;
-      o[0] = fminf(a[0], a[6]); o[1] = fminf(a[1], a[7]); o[2] = fminf(a[2], a[8]);
-      o[3] = fmaxf(a[3], a[9]); o[4] = fmaxf(a[4], a[10]); o[5] = fmaxf(a[5], a[11]);
+      o[0] = fminf(a[0], a[6]); o[1] = fminf(a[1], a[7]); o[4] = fminf(a[4], a[10]);
+      o[2] = fmaxf(a[2], a[8]); o[3] = fmaxf(a[3], a[9]); o[5] = fmaxf(a[5], a[11]);
     }
     __syncthreads();
   }
@@ -267,8 +269,8 @@ shift_index_kernel(const ShiftJob* __restrict__ jobs, const float* __restrict__ 
     const float* a = job.src_nodes + (size_t)i * 6;
     float* o = job.dst_nodes + (size_t)i * 6;
     // empty boxes (+inf / -inf) stay empty
-    o[0] = __fsub_rn(a[0], sx); o[1] = __fsub_rn(a[1], sy); o[2] = __fsub_rn(a[2], sz);
-    o[3] = __fsub_rn(a[3], sx); o[4] = __fsub_rn(a[4], sy); o[5] = __fsub_rn(a[5], sz);
+    o[0] = __fsub_rn(a[0], sx); o[1] = __fsub_rn(a[1], sy); o[2] = __fsub_rn(a[2], sx);
+    o[3] = __fsub_rn(a[3], sy); o[4] = __fsub_rn(a[4], sz); o[5] = __fsub_rn(a[5], sz);
   }
 }
 }  // namespace

@@ -77,10 +77,11 @@ __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float
   if (leaf >= t.n_leaves) return;
   const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
   const int base = leaf * kLeaf;
+  const unsigned long long qxy = pack_f32x2(qx, qy);
 #pragma unroll
   for (int j = 0; j < kLeaf; ++j) {
-    float4 p = lp[j];
-    float dd = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+    float4 p = __ldg(lp + j);
+    float dd = dist2_rn_packed(qxy, qz, p.x, p.y, p.z);
     const int pos = base + j;
     if (dd <= maxr2 && (pos < skip_lo || pos > skip_hi)) acc.offer(dd, __float_as_int(p.w), pos);
   }
@@ -92,16 +93,18 @@ __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float
 template <class Acc>
 __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned node, int depth, float qx, float qy,
                                                   float qz, float maxr2, Acc& acc, int skip_lo, int skip_hi) {
-  const float4* __restrict__ nodes4 = reinterpret_cast<const float4*>(t.nodes);
+  const ulonglong2* __restrict__ nodes16 = reinterpret_cast<const ulonglong2*>(t.nodes);
+  const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
+  const QueryPk q = pack_query(qx, qy, qz);
   unsigned trail = 0;
   while (true) {
     // ---- descend while the nearer child qualifies -------------------------
     bool at_leaf = true;
     while (depth < t.depth) {
-      const float4* __restrict__ c = nodes4 + (size_t)node * 3;  // both children: 48 bytes
-      float4 a = c[0], b = c[1], e = c[2];
-      float lb0 = box_lb_rn(qx, qy, qz, a.x, a.y, a.z, a.w, b.x, b.y);
-      float lb1 = box_lb_rn(qx, qy, qz, b.z, b.w, e.x, e.y, e.z, e.w);
+      const ulonglong2* __restrict__ c = nodes16 + (size_t)node * 3;  // both children: 48 bytes
+      const ulonglong2 a = __ldg(c), b = __ldg(c + 1), e = __ldg(c + 2);
+      float lb0 = box_lb_packed(q, a.x, a.y, b.x);
+      float lb1 = box_lb_packed(q, b.y, e.x, e.y);
       float bound = fminf(acc.bound(), maxr2);
       bool near1 = lb1 < lb0;
       float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
@@ -120,8 +123,8 @@ __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned no
       trail >>= up;
       node ^= 1u;
       trail ^= 1u;
-      const float* __restrict__ nb = t.nodes + (size_t)node * 6;
-      float lb = box_lb_rn(qx, qy, qz, nb[0], nb[1], nb[2], nb[3], nb[4], nb[5]);
+      const unsigned long long* __restrict__ nb = nodes8 + (size_t)node * 3;
+      float lb = box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2));
       if (lb <= fminf(acc.bound(), maxr2)) break;
     }
   }
@@ -149,6 +152,8 @@ __device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx,
   unsigned node = (unsigned)(t.P + leaf);
   int depth = t.depth;
   const float inf = __int_as_float(0x7f800000);
+  const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
+  const QueryPk q = pack_query(qx, qy, qz);
   while (depth > 0) {
     float lbv[4];
 #pragma unroll
@@ -156,9 +161,8 @@ __device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx,
       lbv[u] = inf;
       if (depth - u > 0) {
         const unsigned sib = (node >> u) ^ 1u;
-        const float2* __restrict__ nb = reinterpret_cast<const float2*>(t.nodes + (size_t)sib * 6);
-        float2 a = nb[0], b = nb[1], c = nb[2];
-        lbv[u] = box_lb_rn(qx, qy, qz, a.x, a.y, b.x, b.y, c.x, c.y);
+        const unsigned long long* __restrict__ nb = nodes8 + (size_t)sib * 3;
+        lbv[u] = box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2));
       }
     }
 #pragma unroll 1
