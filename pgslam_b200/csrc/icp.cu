@@ -430,14 +430,14 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   float4 r = v.reading[i];
   float3 q = xform_rn(T, r.x, r.y, r.z);
   Best1 acc;
-  acc.init();
+  acc.init(maxr2);
   // temporal coherence: after the first iteration the previous match is almost
   // always still the answer, so search bottom-up from its leaf
   const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
-  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, maxr2, acc);
-  else knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
+  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc);
+  else knn_traverse(v.tree, q.x, q.y, q.z, acc);
   v.match_pos[i] = acc.pos;
-  v.match_d2[i] = acc.d;
+  v.match_d2[i] = acc.dist();
 }
 
 // KDTreeMatcher knn > 1: every reading point keeps its K nearest (ascending, ties -> lower
@@ -455,10 +455,10 @@ match_k_kernel(const PairView* __restrict__ views, PairState* __restrict__ state
   float4 r = v.reading[i];
   float3 q = xform_rn(T, r.x, r.y, r.z);
   BestK<K> acc;
-  acc.init();
+  acc.init(maxr2);
   const int pp = st.iterations > 0 ? v.match_pos[(size_t)i * k] : -1;
-  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, maxr2, acc);
-  else knn_traverse(v.tree, q.x, q.y, q.z, maxr2, acc);
+  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc);
+  else knn_traverse(v.tree, q.x, q.y, q.z, acc);
   int* op = v.match_pos + (size_t)i * k;
   float* od = v.match_d2 + (size_t)i * k;
 #pragma unroll

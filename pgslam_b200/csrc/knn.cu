@@ -29,7 +29,7 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   if (j >= job.nq) return;
   const float4 q = job.queries[j];
   BestK<K> acc;
-  acc.init();
+  acc.init(maxr2);
   if (job.self) {
     // neighbours in Morton order are mostly neighbours in space: they give a
     // tight k-th distance before the tree is touched, so the climb from the
@@ -38,11 +38,11 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
     for (int p = skip_lo; p <= skip_hi; ++p) {
       float4 c = job.tree.pts[p];
       float dd = dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z);
-      if (dd <= maxr2) acc.offer(dd, __float_as_int(c.w), p);
+      acc.offer(dd, __float_as_int(c.w), p);
     }
-    knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, maxr2, acc, skip_lo, skip_hi);
+    knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, acc, skip_lo, skip_hi);
   } else {
-    knn_traverse(job.tree, q.x, q.y, q.z, maxr2, acc);
+    knn_traverse(job.tree, q.x, q.y, q.z, acc);
   }
   const int col = job.qperm ? job.qperm[j] : j;
   int32_t* oi = job.ids + (size_t)col * k;
@@ -52,7 +52,7 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
     if (e < k) {
       const int id = key_id(acc.key[e]);
       oi[e] = (id == 0x7fffffff) ? -1 : id;
-      od[e] = key_dist(acc.key[e]);
+      od[e] = (id == 0x7fffffff) ? __int_as_float(0x7f800000) : key_dist(acc.key[e]);
     }
   }
 }

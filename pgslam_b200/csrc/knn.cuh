@@ -35,28 +35,33 @@ __device__ __forceinline__ unsigned long long make_key(float d, int id) {
 __device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
 __device__ __forceinline__ int key_id(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull); }
 
+// The matcher's maxDist is folded into the initial state: every slot starts as the key
+// (maxDist^2, INT_MAX), so a candidate farther than maxDist never wins, one exactly at
+// maxDist does (its index is below INT_MAX), and neither the leaf scan nor the box tests need
+// a separate radius compare.  A slot still holding INT_MAX at the end means "not found".
 struct Best1 {
-  float d;
-  int id;
+  unsigned long long key;  // (distance bits << 32) | original index
   int pos;
-  __device__ __forceinline__ void init() {
-    d = __int_as_float(0x7f800000);
-    id = 0x7fffffff;
+  __device__ __forceinline__ void init(float maxr2) {
+    key = make_key(maxr2, 0x7fffffff);
     pos = -1;
   }
-  __device__ __forceinline__ float bound() const { return d; }
+  __device__ __forceinline__ float bound() const { return key_dist(key); }
   __device__ __forceinline__ void offer(float dd, int iid, int ppos) {
-    if (dd < d || (dd == d && iid < id)) { d = dd; id = iid; pos = ppos; }
+    const unsigned long long nk = make_key(dd, iid);
+    if (nk < key) { key = nk; pos = ppos; }
   }
+  // squared distance of the result; +inf when nothing lies within maxDist
+  __device__ __forceinline__ float dist() const { return pos < 0 ? __int_as_float(0x7f800000) : key_dist(key); }
 };
 
 // ascending list of exactly K keys, held in registers (all indices static)
 template <int K>
 struct BestK {
   unsigned long long key[K];
-  __device__ __forceinline__ void init() {
+  __device__ __forceinline__ void init(float maxr2) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) key[j] = kEmptyKey;
+    for (int j = 0; j < K; ++j) key[j] = make_key(maxr2, 0x7fffffff);
   }
   __device__ __forceinline__ float bound() const { return key_dist(key[K - 1]); }
   __device__ __forceinline__ void offer(float dd, int iid, int) {
@@ -72,7 +77,7 @@ struct BestK {
 };
 
 template <class Acc>
-__device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float qx, float qy, float qz, float maxr2,
+__device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float qx, float qy, float qz,
                                               Acc& acc, int skip_lo, int skip_hi) {
   if (leaf >= t.n_leaves) return;
   const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
@@ -83,7 +88,7 @@ __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float
     float4 p = __ldg(lp + j);
     float dd = dist2_rn_packed(qxy, qz, p.x, p.y, p.z);
     const int pos = base + j;
-    if (dd <= maxr2 && (pos < skip_lo || pos > skip_hi)) acc.offer(dd, __float_as_int(p.w), pos);
+    if (pos < skip_lo || pos > skip_hi) acc.offer(dd, __float_as_int(p.w), pos);
   }
 }
 
@@ -92,7 +97,7 @@ __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float
 // caller has already offered (pass an empty range (0, -1) otherwise).
 template <class Acc>
 __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned node, int depth, float qx, float qy,
-                                                  float qz, float maxr2, Acc& acc, int skip_lo, int skip_hi) {
+                                                  float qz, Acc& acc, int skip_lo, int skip_hi) {
   const ulonglong2* __restrict__ nodes16 = reinterpret_cast<const ulonglong2*>(t.nodes);
   const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
   const QueryPk q = pack_query(qx, qy, qz);
@@ -105,7 +110,7 @@ __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned no
       const ulonglong2 a = __ldg(c), b = __ldg(c + 1), e = __ldg(c + 2);
       float lb0 = box_lb_packed(q, a.x, a.y, b.x);
       float lb1 = box_lb_packed(q, b.y, e.x, e.y);
-      float bound = fminf(acc.bound(), maxr2);
+      const float bound = acc.bound();
       bool near1 = lb1 < lb0;
       float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
       if (!(lbn <= bound)) { at_leaf = false; break; }
@@ -113,7 +118,7 @@ __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned no
       node = node * 2 + (near1 ? 1u : 0u);
       ++depth;
     }
-    if (at_leaf) knn_scan_leaf(t, (int)node - t.P, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+    if (at_leaf) knn_scan_leaf(t, (int)node - t.P, qx, qy, qz, acc, skip_lo, skip_hi);
     // ---- walk back to the deepest pending sibling whose box still qualifies --
     while (true) {
       if (trail == 0) return;
@@ -125,16 +130,16 @@ __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned no
       trail ^= 1u;
       const unsigned long long* __restrict__ nb = nodes8 + (size_t)node * 3;
       float lb = box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2));
-      if (lb <= fminf(acc.bound(), maxr2)) break;
+      if (lb <= acc.bound()) break;
     }
   }
 }
 
 // top-down search from the root (no prior knowledge about the query)
 template <class Acc>
-__device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz, float maxr2,
+__device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz,
                                              Acc& acc, int skip_lo = 0, int skip_hi = -1) {
-  knn_traverse_from(t, 1u, 0, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+  knn_traverse_from(t, 1u, 0, qx, qy, qz, acc, skip_lo, skip_hi);
 }
 
 // Bottom-up search from a seed leaf (last iteration's match, or the query's own
@@ -146,9 +151,9 @@ __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float 
 // union of the seed leaf and all sibling subtrees is the whole tree, so the
 // result is the same exact minimum as the top-down walk.
 template <class Acc>
-__device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx, float qy, float qz, float maxr2,
+__device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx, float qy, float qz,
                                           Acc& acc, int skip_lo = 0, int skip_hi = -1) {
-  knn_scan_leaf(t, leaf, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+  knn_scan_leaf(t, leaf, qx, qy, qz, acc, skip_lo, skip_hi);
   unsigned node = (unsigned)(t.P + leaf);
   int depth = t.depth;
   const float inf = __int_as_float(0x7f800000);
@@ -169,8 +174,8 @@ __device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx,
     for (int u = 0; u < 4; ++u) {
       const float lb = u == 0 ? lbv[0] : (u == 1 ? lbv[1] : (u == 2 ? lbv[2] : lbv[3]));
       // an empty box has lb = +inf: the `< inf` test keeps an unbounded first search out of it
-      if (lb < inf && lb <= fminf(acc.bound(), maxr2))
-        knn_traverse_from(t, (node >> u) ^ 1u, depth - u, qx, qy, qz, maxr2, acc, skip_lo, skip_hi);
+      if (lb < inf && lb <= acc.bound())
+        knn_traverse_from(t, (node >> u) ^ 1u, depth - u, qx, qy, qz, acc, skip_lo, skip_hi);
     }
     node >>= 4;
     depth -= 4;
