@@ -242,14 +242,17 @@ def main():
         return rds, rfs
 
     pending = []
+    e2e_wall = []  # host wall-clock of every e2e step (warm-up included), for the record
 
     def step_e2e():
         # software pipeline: this step's inputs were queued on the copy stream while the
         # previous step computed; every step still uploads its own inputs and downloads its results
+        t0 = time.perf_counter()
         rds, rfs = pending.pop() if pending else upload()
         pending.append(upload())
         res = icp.compute_batch(rds, rfs)
         gather(res)
+        e2e_wall.append(round(1e3 * (time.perf_counter() - t0), 2))
         return res
 
     def barrier():
@@ -272,6 +275,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, out
+
+    # a generation-2 Python garbage collection in a process that has imported torch takes ~35 ms
+    # (measured: one e2e step in ~15 doubled); the steps allocate nothing cyclic, so the
+    # collector is parked for the measurement instead of being timed
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
 
     # clocks are sampled from the warm-up steps on (same load as the timed steps): the
     # timed region alone is ~100 ms, too short for more than a sample or two
@@ -356,7 +367,8 @@ def main():
                        "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
                        "parallelism": f"{world} GPU(s), independent pairs per rank, NCCL all_gather of 4x4 results"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
-                    "d2h_bytes_per_step": int(total_pairs * 480), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(total_pairs * 480), "ms_per_step": ms_e2e / args.steps,
+                    "wall_ms_each_step_incl_warmup": e2e_wall},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "iterations_mean": statistics.mean(iters), "pairs_ok": ok,
             "single_pair_latency_ms": ms_one / 10.0}

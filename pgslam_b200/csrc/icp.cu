@@ -419,6 +419,24 @@ gather_vec3_sorted_kernel(const float4* __restrict__ sorted_pts, int n, const fl
   else out1[j] = src[o];
 }
 
+// the same for the span-3 descriptor of every reference of a batch in one launch
+struct GatherJob {
+  const float4* sorted_pts;
+  const float* src;
+  float4* out4;
+  int n;
+};
+__global__ void __launch_bounds__(256) gather_vec3_sorted_batched_kernel(const GatherJob* __restrict__ jobs) {
+  const GatherJob job = jobs[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= job.n) return;
+  const int o = __float_as_int(job.sorted_pts[j].w);
+  job.out4[j] = make_float4(job.src[3 * o], job.src[3 * o + 1], job.src[3 * o + 2], 0.f);
+}
+
+#ifndef PGS_SEED_GROUP
+#define PGS_SEED_GROUP 0
+#endif
 __global__ void PGS_MATCH_BOUNDS
 match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
   PairState& st = states[blockIdx.y];
@@ -434,7 +452,7 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   // temporal coherence: after the first iteration the previous match is almost
   // always still the answer, so search bottom-up from its leaf
   const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
-  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc);
+  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc, 0, -1, PGS_SEED_GROUP);
   else knn_traverse(v.tree, q.x, q.y, q.z, acc);
   v.match_pos[i] = acc.pos;
   v.match_d2[i] = acc.dist();
@@ -1268,6 +1286,8 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
   std::vector<double> hT((size_t)16 * B);
   Tmean.download(hT.data(), hT.size());
   out.clear();
+  std::vector<GatherJob> gjobs;
+  int gmax = 0;
   for (int b = 0; b < B; ++b) {
     auto pr = std::make_unique<PreparedRef>();
     pr->index = std::move(idx[b]);
@@ -1275,9 +1295,8 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     pr->has_normals = nrm != nullptr;
     if (nrm && ns[b] > 0) {
       pr->normals_sorted.reset(ctx, (size_t)ns[b]);
-      gather_vec3_sorted_kernel<<<ceil_div(ns[b], 256), 256, 0, s>>>(pr->index->pts.p, ns[b], nrm->data.p, 3,
-                                                                    pr->normals_sorted.p, nullptr);
-      ctx_count_launches(ctx, 1);
+      gjobs.push_back(GatherJob{pr->index->pts.p, nrm->data.p, pr->normals_sorted.p, ns[b]});
+      gmax = std::max(gmax, ns[b]);
     }
     if (params_.knn > 1 && ns[b] > 0) {
       pr->inv_pos.reset(ctx, (size_t)ns[b]);
@@ -1286,6 +1305,12 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     }
     pr->cloud = std::move(refs[b]);
     out.push_back(std::move(pr));
+  }
+  DBuf<GatherJob> d_gjobs(ctx, std::max<size_t>(gjobs.size(), 1));
+  if (!gjobs.empty()) {
+    ctx->upload_small(d_gjobs.p, gjobs.data(), sizeof(GatherJob) * gjobs.size());
+    gather_vec3_sorted_batched_kernel<<<dim3(ceil_div(gmax, 256), (unsigned)gjobs.size()), 256, 0, s>>>(d_gjobs.p);
+    ctx_count_launches(ctx, 1);
   }
   ctx->sync();  // Tmean on the host (one sync per prepare, not per iteration)
   for (int b = 0; b < B; ++b) std::memcpy(out[b]->T_refIn_refMean, hT.data() + 16 * b, 16 * sizeof(double));

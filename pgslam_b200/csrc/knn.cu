@@ -11,6 +11,10 @@ namespace pgs {
 
 namespace {
 
+#ifndef PGS_SELF_GROUP
+#define PGS_SELF_GROUP 1
+#endif
+
 struct KnnJobDev {
   TreeView tree;
   const float4* queries;
@@ -30,6 +34,14 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   const float4 q = job.queries[j];
   BestK<K> acc;
   acc.init(maxr2);
+  if (job.self && K <= kSeedSlots && PGS_SELF_GROUP >= 0) {
+    // the lanes that share a group of leaves share its candidates: sort them once per lane
+    // without a branch, then climb from above the group on a path those lanes have in common
+    if constexpr (K <= kSeedSlots) {
+      knn_seed_group<K>(job.tree, j / kLeaf, PGS_SELF_GROUP, q.x, q.y, q.z, maxr2, acc);
+      knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, acc, 0, -1, PGS_SELF_GROUP, false);
+    }
+  } else
   if (job.self) {
     // neighbours in Morton order are mostly neighbours in space: they give a
     // tight k-th distance before the tree is touched, so the climb from the
@@ -44,7 +56,8 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   } else {
     knn_traverse(job.tree, q.x, q.y, q.z, acc);
   }
-  const int col = job.qperm ? job.qperm[j] : j;
+  // a self-search's queries are the index' own points: .w is the original index = the result column
+  const int col = job.self ? __float_as_int(q.w) : (job.qperm ? job.qperm[j] : j);
   int32_t* oi = job.ids + (size_t)col * k;
   float* od = job.d2 + (size_t)col * k;
 #pragma unroll
@@ -55,11 +68,6 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
       od[e] = (id == 0x7fffffff) ? __int_as_float(0x7f800000) : key_dist(acc.key[e]);
     }
   }
-}
-
-__global__ void perm_from_sorted_kernel(const float4* __restrict__ pts, int n, int* __restrict__ perm) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) perm[j] = __float_as_int(pts[j].w);
 }
 
 template <int K>
@@ -107,17 +115,8 @@ void knn_self_batched(Ctx* ctx, const std::vector<const Index*>& idx, int k, flo
                       const std::vector<int32_t*>& ids, const std::vector<float*>& d2) {
   // queries = the index' own sorted points; column = original index (pts.w)
   std::vector<KnnJobDev> dj;
-  std::vector<DBuf<int>> perms;
-  perms.reserve(idx.size());
-  for (size_t b = 0; b < idx.size(); ++b) {
-    perms.emplace_back(ctx, (size_t)std::max(idx[b]->n, 1));
-    if (idx[b]->n > 0) {
-      perm_from_sorted_kernel<<<ceil_div(idx[b]->n, 256), 256, 0, ctx->stream>>>(idx[b]->pts.p, idx[b]->n,
-                                                                                 perms.back().p);
-      ctx_count_launches(ctx, 1);
-    }
-    dj.push_back(KnnJobDev{idx[b]->view(), idx[b]->pts.p, perms.back().p, idx[b]->n, ids[b], d2[b], 1});
-  }
+  for (size_t b = 0; b < idx.size(); ++b)
+    dj.push_back(KnnJobDev{idx[b]->view(), idx[b]->pts.p, nullptr, idx[b]->n, ids[b], d2[b], 1});
   launch(ctx, dj, k, max_dist);
 }
 

@@ -76,6 +76,59 @@ struct BestK {
   }
 };
 
+// Batcher's odd-even merge sort of 16 keys held in registers (63 compare-exchanges, checked
+// with the 0-1 principle by the generator): every index is a literal, so the array never
+// leaves the register file.
+__device__ __forceinline__ void sort_keys_network16(unsigned long long (&a)[16]) {
+#define PGS_CSWAP(i, j)                                  \
+  {                                                      \
+    const unsigned long long x = a[i], y = a[j];         \
+    const bool sw = y < x;                               \
+    a[i] = sw ? y : x;                                   \
+    a[j] = sw ? x : y;                                   \
+  }
+  PGS_CSWAP(0, 1); PGS_CSWAP(2, 3); PGS_CSWAP(4, 5); PGS_CSWAP(6, 7); PGS_CSWAP(8, 9); PGS_CSWAP(10, 11);
+  PGS_CSWAP(12, 13); PGS_CSWAP(14, 15); PGS_CSWAP(0, 2); PGS_CSWAP(1, 3); PGS_CSWAP(4, 6); PGS_CSWAP(5, 7);
+  PGS_CSWAP(8, 10); PGS_CSWAP(9, 11); PGS_CSWAP(12, 14); PGS_CSWAP(13, 15); PGS_CSWAP(1, 2); PGS_CSWAP(5, 6);
+  PGS_CSWAP(9, 10); PGS_CSWAP(13, 14); PGS_CSWAP(0, 4); PGS_CSWAP(1, 5); PGS_CSWAP(2, 6); PGS_CSWAP(3, 7);
+  PGS_CSWAP(8, 12); PGS_CSWAP(9, 13); PGS_CSWAP(10, 14); PGS_CSWAP(11, 15); PGS_CSWAP(2, 4); PGS_CSWAP(3, 5);
+  PGS_CSWAP(10, 12); PGS_CSWAP(11, 13); PGS_CSWAP(1, 2); PGS_CSWAP(3, 4); PGS_CSWAP(5, 6); PGS_CSWAP(9, 10);
+  PGS_CSWAP(11, 12); PGS_CSWAP(13, 14); PGS_CSWAP(0, 8); PGS_CSWAP(1, 9); PGS_CSWAP(2, 10); PGS_CSWAP(3, 11);
+  PGS_CSWAP(4, 12); PGS_CSWAP(5, 13); PGS_CSWAP(6, 14); PGS_CSWAP(7, 15); PGS_CSWAP(4, 8); PGS_CSWAP(5, 9);
+  PGS_CSWAP(6, 10); PGS_CSWAP(7, 11); PGS_CSWAP(2, 4); PGS_CSWAP(3, 5); PGS_CSWAP(6, 8); PGS_CSWAP(7, 9);
+  PGS_CSWAP(10, 12); PGS_CSWAP(11, 13); PGS_CSWAP(1, 2); PGS_CSWAP(3, 4); PGS_CSWAP(5, 6); PGS_CSWAP(7, 8);
+  PGS_CSWAP(9, 10); PGS_CSWAP(11, 12); PGS_CSWAP(13, 14);
+#undef PGS_CSWAP
+}
+
+// Seed of a self-search: the aligned group of 2^group leaves (<= kSeedSlots points) around the
+// query's own leaf is the same for all the lanes that share it, so instead of offering its
+// points one by one (a divergent insertion each) every lane sorts the whole group's keys with
+// a branch-free network and keeps the K smallest.  maxr2 caps the list as in BestK::init.
+constexpr int kSeedSlots = 16;  // = the network's width
+template <int K>
+__device__ __forceinline__ void knn_seed_group(const TreeView& t, int leaf, int group, float qx, float qy, float qz,
+                                               float maxr2, BestK<K>& acc) {
+  static_assert(K <= kSeedSlots, "the seed group must hold at least K points");
+  group = min(group, t.depth);
+  const int first = (leaf & ~((1 << group) - 1)) * kLeaf;
+  const int count = min(kLeaf << group, t.n_leaves * kLeaf - first);
+  const unsigned long long qxy = pack_f32x2(qx, qy);
+  unsigned long long a[kSeedSlots];
+#pragma unroll
+  for (int j = 0; j < kSeedSlots; ++j) {
+    a[j] = kEmptyKey;
+    if (j < count) {
+      const float4 p = __ldg(t.pts + first + j);
+      a[j] = make_key(dist2_rn_packed(qxy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    }
+  }
+  sort_keys_network16(a);
+  const unsigned long long cap = make_key(maxr2, 0x7fffffff);
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc.key[j] = a[j] < cap ? a[j] : cap;
+}
+
 template <class Acc>
 __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float qx, float qy, float qz,
                                               Acc& acc, int skip_lo, int skip_hi) {
@@ -150,12 +203,23 @@ __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float 
 // seed almost every sibling fails its bound test and is never entered.  The
 // union of the seed leaf and all sibling subtrees is the whole tree, so the
 // result is the same exact minimum as the top-down walk.
+// `group` > 0 widens the seed from one leaf to the aligned group of 2^group leaves around it
+// (scanned by every lane in lock step) and starts the climb `group` levels higher: the
+// lowest siblings are the ones a query pokes into most often, and entering them one lane
+// at a time costs far more issue slots than scanning them uniformly.
 template <class Acc>
 __device__ __forceinline__ void knn_climb(const TreeView& t, int leaf, float qx, float qy, float qz,
-                                          Acc& acc, int skip_lo = 0, int skip_hi = -1) {
-  knn_scan_leaf(t, leaf, qx, qy, qz, acc, skip_lo, skip_hi);
-  unsigned node = (unsigned)(t.P + leaf);
-  int depth = t.depth;
+                                          Acc& acc, int skip_lo = 0, int skip_hi = -1, int group = 0,
+                                          bool scan_seed = true) {
+  group = min(group, t.depth);
+  if (scan_seed) {
+    const int first = leaf & ~((1 << group) - 1);
+    knn_scan_leaf(t, leaf, qx, qy, qz, acc, skip_lo, skip_hi);
+    for (int l = first; l < first + (1 << group); ++l)
+      if (l != leaf) knn_scan_leaf(t, l, qx, qy, qz, acc, skip_lo, skip_hi);
+  }
+  unsigned node = (unsigned)(t.P + leaf) >> group;
+  int depth = t.depth - group;
   const float inf = __int_as_float(0x7f800000);
   const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
   const QueryPk q = pack_query(qx, qy, qz);

@@ -8,7 +8,8 @@ torch.cuda.set_device(0)
 stream = torch.cuda.current_stream()
 ctx = pm.Context(0, stream.cuda_stream)
 icp = pm.ICP(ctx); icp.loadFromYaml(util.to_yaml(util.C2))
-B = 48
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+ctx.set_batch_streams(int(sys.argv[2]) if len(sys.argv) > 2 else 4)
 pairs = bench.gen_pairs(range(B))
 host = [(torch.from_numpy(np.ascontiguousarray(rd.T)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rf.T)).pin_memory()) for rd, rf in pairs]
 def upload():
