@@ -29,6 +29,7 @@ namespace {
 
 constexpr int kLocal = 4096;       // points finished by one block in shared memory
 constexpr int kLocalThreads = 1024;
+constexpr int kFineLevels = 2;     // global levels sorted on 16-bit keys; the ones below use 8 bits
 
 struct KdCloud {
   const float4* pts;
@@ -92,7 +93,7 @@ __device__ __forceinline__ int widest_axis(const unsigned* bb) {
 
 __global__ void __launch_bounds__(256)
 kd_key_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ vals, int span, int segs, int S,
-              const unsigned* __restrict__ bbox, uint32_t* __restrict__ keys) {
+              const unsigned* __restrict__ bbox, uint32_t* __restrict__ keys, float key_max) {
   const int j = blockIdx.y;
   const int b = j / segs, s = j % segs;
   const KdCloud c = clouds[b];
@@ -103,23 +104,24 @@ kd_key_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ v
   const int axis = widest_axis(bb);
   const size_t o = (size_t)b * span + (size_t)s * S + i;
   float4 p = c.pts[vals[o]];
-  // 16-bit key: the coordinate quantised over the segment's own extent.  Any
-  // order yields a valid tree (boxes come from the points); a split that is off
-  // by one 1/65536th of the extent costs nothing measurable and halves the
-  // number of radix passes per level.
+  // key: the coordinate quantised over the segment's own extent, 16 bits (two radix passes)
+  // at the two top levels, 8 bits (one pass) below.  Any order yields a valid tree (boxes
+  // come from the points); points inside the median's bin are split by position, so the
+  // sibling boxes may overlap by one bin: 1/65536th of a 60 m extent at the top, 1/256th of
+  // a 30 m one (12 cm) at level 2 - a slab that holds well under 1 % of the queries.
   const float lo = ord2f(bb[axis]), hi = ord2f(bb[3 + axis]);
   const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
-  const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
+  const float scale = hi > lo ? key_max / (hi - lo) : 0.f;
   int q = (int)((x - lo) * scale);
-  keys[o] = (uint32_t)max(0, min(65535, q));
+  keys[o] = (uint32_t)max(0, min((int)key_max, q));
 }
 
 // ---- local levels: one block owns m0 (<= kLocal) consecutive slots ------------
 //
 // Sub-segments of kRadixMin points or more are SPLIT, not sorted: only the median
 // partition matters (both halves are re-split along their own axis one level
-// down).  Per level: bounding box -> widest axis -> 16-bit key -> two 256-bin
-// histogram passes find the exact median key and how many of its ties go left
+// down).  Per level: bounding box -> widest axis -> 8-bit key -> one 256-bin
+// histogram pass finds the median's bin and how many of its members go left
 // -> one stable partition pass (per-32-chunk counts + prefix, deterministic).
 // Smaller sub-segments are sorted with a bitonic network whose strides stay
 // inside a warp's window, so they need almost no block barriers.
@@ -128,7 +130,8 @@ constexpr int kMaxRadixSegs = kLocal / kRadixMin;  // 16
 constexpr int kChunks = kLocal / 32;               // 128
 
 __global__ void __launch_bounds__(kLocalThreads)
-kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals, int span, int segs, int m0) {
+kd_local_kernel(const KdCloud* __restrict__ clouds, const uint32_t* vals, uint32_t* vals_out, int span, int segs,
+                int m0) {
   extern __shared__ unsigned smem[];
   unsigned* sx = smem;                 // ordered-uint coordinates, fixed slots
   unsigned* sy = sx + kLocal;
@@ -154,7 +157,8 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
   const KdCloud c = clouds[b];
   const int cnt = seg_count(c.n, s, m0);
   if (cnt == 0) return;
-  uint32_t* v = vals + (size_t)b * span + (size_t)s * m0;
+  const uint32_t* v = vals + (size_t)b * span + (size_t)s * m0;
+  uint32_t* vo = vals_out + (size_t)b * span + (size_t)s * m0;  // may alias v: gather, barrier, write
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned short* perm = perm_a;
   unsigned short* perm_next = perm_b;
@@ -170,9 +174,11 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
   }
   __syncthreads();
   for (int m = m0; m > kLeaf; m >>= 1) {
-    const int nseg = m0 / m;
+    // m0 and m are powers of two: every i / m below is a shift
+    const int lm = 31 - __clz(m);
+    const int nseg = m0 >> lm;
     // ---- bounding box of every sub-segment (real points only) -> widest axis ----
-    for (int q = tid; q < nseg * 6; q += kLocalThreads) bb[q] = (q % 6 < 3) ? 0xffffffffu : 0u;
+    for (int q = tid; q < nseg * 6; q += kLocalThreads) bb[q] = (q % 6 < 3) ? 0xffffffffu : 0u;  // constant divisor
     __syncthreads();
     for (int i = tid; i < m0; i += kLocalThreads) {
       const int slot = perm[i];
@@ -188,7 +194,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
       }
       const bool leader = m >= 32 ? (tid & 31) == 0 : (tid & 15) == 0;
       if (leader && lo[0] <= hi[0]) {
-        unsigned* q = bb + 6 * (i / m);
+        unsigned* q = bb + 6 * (i >> lm);
 #pragma unroll
         for (int d = 0; d < 3; ++d) { atomicMin(q + d, lo[d]); atomicMax(q + 3 + d, hi[d]); }
       }
@@ -199,42 +205,38 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
 
     if (m >= kRadixMin) {
       // ================= median split by radix select + stable partition =================
-      // 16-bit key: coordinate quantised over the sub-segment's extent; padding = 0xffff
+      // 8-bit key: the coordinate quantised over the sub-segment's own extent (padding = 255).
+      // Points that share the median's bin are split by position, so sibling boxes can overlap
+      // by 1/255 of the extent - millimetres at these levels - which no query notices, and
+      // one histogram pass finds the split.
       for (int i = tid; i < m0; i += kLocalThreads) {
         const int slot = perm[i];
-        const int sg = i / m;
+        const int sg = i >> lm;
         const int a = axis[sg];
-        unsigned k16 = 0xffffu;
+        unsigned k8 = 255u;
         if (slot < cnt) {
           const unsigned* q = bb + 6 * sg;
           const float lo = ord2f(q[a]), hi = ord2f(q[3 + a]);
           const float x = ord2f(a == 0 ? sx[slot] : (a == 1 ? sy[slot] : sz[slot]));
-          const float scale = hi > lo ? 65534.0f / (hi - lo) : 0.f;
-          k16 = (unsigned)max(0, min(65534, (int)((x - lo) * scale)));
+          const float scale = hi > lo ? 254.0f / (hi - lo) : 0.f;
+          k8 = (unsigned)max(0, min(254, (int)((x - lo) * scale)));
         }
-        key[i] = k16;
+        key[i] = k8;
       }
       const int target = m / 2;  // the left child takes the `target` smallest keys
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int q = tid; q < nseg * 256; q += kLocalThreads) hist[q] = 0;
-        __syncthreads();
-        for (int i = tid; i < m0; i += kLocalThreads) {
-          const int sg = i / m;
-          const unsigned k16 = key[i];
-          const bool in = pass == 0 || (int)(k16 >> 8) == seg_b1[sg];
-          const unsigned act = __ballot_sync(0xffffffffu, in);
-          if (in) {
-            const unsigned bin = pass == 0 ? (k16 >> 8) : (k16 & 255u);
-            const unsigned peers = __match_any_sync(act, bin);
-            if (lane == __ffs(peers) - 1) atomicAdd(&hist[sg * 256 + bin], (unsigned)__popc(peers));
-          }
-        }
-        __syncthreads();
+      for (int q = tid; q < nseg * 256; q += kLocalThreads) hist[q] = 0;
+      __syncthreads();
+      for (int i = tid; i < m0; i += kLocalThreads) {
+        const unsigned bin = key[i];
+        const unsigned peers = __match_any_sync(0xffffffffu, bin | ((unsigned)(i >> lm) << 8));
+        if (lane == __ffs(peers) - 1) atomicAdd(&hist[(i >> lm) * 256 + bin], (unsigned)__popc(peers));
+      }
+      __syncthreads();
+      {
         // one warp per sub-segment: smallest bin whose cumulative count reaches the target
         const int w = tid >> 5;
         if (w < nseg) {
           const unsigned* h = hist + w * 256;
-          const int want = pass == 0 ? target : target - seg_below[w];
           int mine[8], sum = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) { mine[j] = (int)h[lane * 8 + j]; sum += mine[j]; }
@@ -244,24 +246,18 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
             int u = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += u;
           }
-          const unsigned reach = __ballot_sync(0xffffffffu, incl >= want);
-          const int sel = __ffs(reach) - 1;  // always found: the segment holds m >= want slots
+          const unsigned reach = __ballot_sync(0xffffffffu, incl >= target);
+          const int sel = __ffs(reach) - 1;  // always found: the segment holds m >= target slots
           if (lane == sel) {
             int cum = incl - sum, j = 0;
             for (; j < 7; ++j) {
-              if (cum + mine[j] >= want) break;
+              if (cum + mine[j] >= target) break;
               cum += mine[j];
             }
-            const int bin = lane * 8 + j;
-            if (pass == 0) {
-              seg_b1[w] = bin;
-              seg_below[w] = cum;
-            } else {
-              seg_kp[w] = (seg_b1[w] << 8) | bin;
-              seg_less[w] = seg_below[w] + cum;
-              seg_eq[w] = mine[j];
-              seg_tie[w] = target - (seg_below[w] + cum);  // ties that still go left (>= 1)
-            }
+            seg_kp[w] = lane * 8 + j;
+            seg_less[w] = cum;
+            seg_eq[w] = mine[j];
+            seg_tie[w] = target - cum;  // ties that still go left (>= 1)
           }
         }
         __syncthreads();
@@ -276,7 +272,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
         my_side[r] = -1;
         my_rank[r] = 0;
         if (r < rounds && i < m0) {
-          const int sg = i / m;
+          const int sg = i >> lm;
           const int k16 = (int)key[i], kp = seg_kp[sg];
           const int side = k16 < kp ? 0 : (k16 == kp ? 1 : 2);
           const unsigned bl = __ballot_sync(0xffffffffu, side == 0);
@@ -290,7 +286,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
       }
       __syncthreads();
       if (tid < m0 / 32) {
-        const int per = m / 32, first = (tid / per) * per;
+        const int first = (tid >> (lm - 5)) << (lm - 5);
         int sl = 0, se = 0;
         for (int c2 = first; c2 < tid; ++c2) { sl += ch_l[c2]; se += ch_e[c2]; }
         ch_ol[tid] = (unsigned short)sl;
@@ -301,7 +297,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
       for (int r = 0; r < kLocal / kLocalThreads; ++r) {
         const int i = r * kLocalThreads + tid;
         if (my_side[r] >= 0) {
-          const int sg = i / m, ch = i >> 5, base = sg * m;
+          const int sg = i >> lm, ch = i >> 5, base = sg << lm;
           const int ol = ch_ol[ch], oe = ch_oe[ch];
           int pos;
           if (my_side[r] == 0) {
@@ -310,7 +306,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
             const int e = oe + my_rank[r], tie = seg_tie[sg];
             pos = e < tie ? base + seg_less[sg] + e : base + target + (e - tie);
           } else {
-            const int og = (ch - sg * (m / 32)) * 32 - ol - oe;
+            const int og = (ch - (sg << (lm - 5))) * 32 - ol - oe;
             pos = base + target + (seg_eq[sg] - seg_tie[sg]) + og + my_rank[r];
           }
           perm_next[pos] = perm[i];
@@ -322,7 +318,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
       // ================= small sub-segments: bitonic sort of (key, perm) ==================
       for (int i = tid; i < m0; i += kLocalThreads) {
         const int slot = perm[i];
-        const int a = axis[i / m];
+        const int a = axis[i >> lm];
         key[i] = a == 0 ? sx[slot] : (a == 1 ? sy[slot] : sz[slot]);
       }
       // Pair t of a stage with stride jj is (i, i|jj), i = t with a zero bit inserted
@@ -361,7 +357,7 @@ kd_local_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals,
 #pragma unroll
   for (int r = 0; r < kLocal / kLocalThreads; ++r) {
     const int i = r * kLocalThreads + tid;
-    if (i < cnt) v[i] = out[r];
+    if (i < cnt) vo[i] = out[r];
   }
 }
 
@@ -383,8 +379,9 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
   ctx->upload_small(clouds.p, hc.data(), sizeof(KdCloud) * B);
   const size_t total = (size_t)B * span;
   DBuf<uint32_t> keys_a(ctx, total), keys_b(ctx, total), vals_b(ctx, total);
-  uint32_t* vals_a = d_vals_out;
-  kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, vals_a, span);
+  uint32_t* cur = d_vals_out;   // the buffer that holds the current order
+  uint32_t* other = vals_b.p;
+  kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, cur, span);
   ctx_count_launches(ctx, 1);
   int level = 0;
   for (; (span >> level) > kLocal; ++level) {
@@ -393,20 +390,22 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
     DBuf<unsigned> bbox(ctx, (size_t)6 * jobs);
     kd_jobs_kernel<<<ceil_div(jobs, 128), 128, 0, st>>>(clouds.p, B, segs, S, job_n.p, bbox.p);
     const int seg_max = std::min(S, max_n);
-    kd_bbox_kernel<<<dim3(std::max(1, std::min(ceil_div(seg_max, 2048), 64)), jobs), 256, 0, st>>>(clouds.p, vals_a, span,
+    kd_bbox_kernel<<<dim3(std::max(1, std::min(ceil_div(seg_max, 2048), 64)), jobs), 256, 0, st>>>(clouds.p, cur, span,
                                                                                                  segs, S, bbox.p);
-    kd_key_kernel<<<dim3(ceil_div(seg_max, 256), jobs), 256, 0, st>>>(clouds.p, vals_a, span, segs, S, bbox.p, keys_a.p);
+    const int key_bits = level < kFineLevels ? 16 : 8;
+    kd_key_kernel<<<dim3(ceil_div(seg_max, 256), jobs), 256, 0, st>>>(clouds.p, cur, span, segs, S, bbox.p, keys_a.p,
+                                                                      (float)((1 << key_bits) - 1));
     ctx_count_launches(ctx, 3);
     // jobs are laid out back to back with stride S: cloud b, segment s starts at (b*segs + s) * S
-    bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, vals_a, vals_b.p, job_n.p, jobs, S, seg_max, 16);
-    if (in_b) throw Error(PGS_CUDA_ERROR, "kd_order: unexpected sort buffer parity");
+    const bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, cur, other, job_n.p, jobs, S, seg_max, key_bits);
+    if (in_b) std::swap(cur, other);  // a one-pass sort leaves the order in the other buffer
   }
   const int m0 = std::min(span, kLocal);
   const int segs = span / m0;
   const size_t smem = (size_t)kLocal * 4 * 4 + 6 * (kLocal / 16) * 4 + (size_t)kMaxRadixSegs * 256 * 4 +
                       6 * kMaxRadixSegs * 4 + (size_t)kLocal * 2 * 2 + 4 * kChunks * 2 + kLocal / 16 + 64;
   PGS_CUDA(cudaFuncSetAttribute(kd_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kd_local_kernel<<<dim3(segs, B), kLocalThreads, smem, st>>>(clouds.p, vals_a, span, segs, m0);
+  kd_local_kernel<<<dim3(segs, B), kLocalThreads, smem, st>>>(clouds.p, cur, d_vals_out, span, segs, m0);
   ctx_count_launches(ctx, 1);
   PGS_LAUNCH_CHECK();
 }
