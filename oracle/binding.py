@@ -20,6 +20,7 @@ OK, CONVERGENCE_ERROR, TRANSFORMATION_ERROR, INVALID_PARAMETER, INVALID_FIELD = 
 F_RANDOM_SAMPLING, F_VOXEL_GRID, F_SURFACE_NORMAL, F_OBSERVATION_DIRECTION = 1, 2, 3, 4
 F_ORIENT_NORMALS, F_SIMPLE_SENSOR_NOISE, F_MAX_DIST, F_MIN_DIST, F_BOUNDING_BOX = 5, 6, 7, 8, 9
 F_MAX_DENSITY, F_SAMPLING_SURFACE_NORMAL = 10, 11
+F_REMOVE_NAN, F_FIX_STEP_SAMPLING, F_SHADOW, F_IDENTITY = 12, 13, 14, 15
 O_TRIMMED_DIST, O_MAX_DIST, O_MIN_DIST, O_MEDIAN_DIST, O_SURFACE_NORMAL = 1, 2, 3, 4, 5
 O_VAR_TRIMMED_DIST = 6
 E_POINT_TO_PLANE, E_POINT_TO_PLANE_WITH_COV, E_POINT_TO_POINT = 1, 2, 3
@@ -272,6 +273,16 @@ def make_filter(name: str, **p) -> CFilter:
         f.type, f.i0 = F_ORIENT_NORMALS, int(p.get("towardCenter", 1))
     elif name == "SimpleSensorNoiseDataPointsFilter":
         f.type, f.i0, f.p0 = F_SIMPLE_SENSOR_NOISE, int(p.get("sensorType", 0)), float(p.get("gain", 1.0))
+    elif name == "IdentityDataPointsFilter":
+        f.type = F_IDENTITY
+    elif name == "RemoveNaNDataPointsFilter":
+        f.type = F_REMOVE_NAN
+    elif name == "FixStepSamplingDataPointsFilter":
+        if float(p.get("stepMult", 1)) != 1 or int(p.get("endStep", p.get("startStep", 10))) != int(p.get("startStep", 10)):
+            raise KeyError("FixStepSampling: step schedules are not supported")
+        f.type, f.i0, f.i1 = F_FIX_STEP_SAMPLING, int(p.get("startStep", 10)), int(p.get("seed", 0))
+    elif name == "ShadowDataPointsFilter":
+        f.type, f.p0 = F_SHADOW, float(p.get("eps", 0.1))
     elif name == "MaxDistDataPointsFilter":
         f.type, f.i0, f.p0 = F_MAX_DIST, int(p.get("dim", -1)), float(p.get("maxDist", 1.0))
     elif name == "MinDistDataPointsFilter":

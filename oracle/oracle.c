@@ -943,6 +943,65 @@ static int filter_bounding_box(const orc_filter *f, orc_cloud *c) {
   return ORC_OK;
 }
 
+static int filter_remove_nan(orc_cloud *c) {
+  /* RemoveNaNDataPointsFilter [UPSTREAM-RECALLED, DataPointsFilters/RemoveNaN.cpp]:
+   * a point survives iff none of its coordinates is NaN; order preserved.     */
+  int64_t *keep = (int64_t *)malloc((size_t)(c->n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = 0; i < c->n; ++i) {
+    const float *p = c->feat + 4 * i;
+    if (!(isnan(p[0]) || isnan(p[1]) || isnan(p[2]))) keep[m++] = i;
+  }
+  cloud_select(c, keep, m);
+  free(keep);
+  return ORC_OK;
+}
+
+static int filter_fix_step_sampling(const orc_filter *f, orc_cloud *c) {
+  /* FixStepSamplingDataPointsFilter [UPSTREAM-RECALLED, DataPointsFilters/FixStepSampling.cpp]
+   * with stepMult = 1 (constant step): keeps points phase, phase+step, ...; upstream draws
+   * the phase with rand() % step, here it is a hash of the seed.            */
+  int64_t step = f->i0 < 1 ? 1 : f->i0;
+  int64_t phase = (int64_t)(splitmix64(splitmix64((uint64_t)f->i1)) % (uint64_t)step);
+  int64_t *keep = (int64_t *)malloc((size_t)(c->n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = phase; i < c->n; i += step) keep[m++] = i;
+  cloud_select(c, keep, m);
+  free(keep);
+  return ORC_OK;
+}
+
+static int filter_shadow(const orc_filter *f, orc_cloud *c) {
+  /* ShadowDataPointsFilter [UPSTREAM-RECALLED, DataPointsFilters/Shadow.cpp]: a point whose
+   * normal is (nearly) perpendicular to the ray from the origin lies on a grazing surface or
+   * a depth discontinuity; keep iff |normalized(normal) . normalized(point)| > eps.
+   * fp32, sums in x,y,z order, v / sqrt(v.v) (a zero vector stays zero).               */
+  if (!c->normals) return ORC_INVALID_FIELD;
+  float eps = (float)f->p0;
+  int64_t *keep = (int64_t *)malloc((size_t)(c->n + 1) * sizeof(int64_t));
+  int64_t m = 0;
+  for (int64_t i = 0; i < c->n; ++i) {
+    const float *p = c->feat + 4 * i, *nr = c->normals + 3 * i;
+    float v[2][3] = {{nr[0], nr[1], nr[2]}, {p[0], p[1], p[2]}};
+    for (int k = 0; k < 2; ++k) {
+      float s = v[k][0] * v[k][0];
+      s = s + v[k][1] * v[k][1];
+      s = s + v[k][2] * v[k][2];
+      if (s > 0.0f) {
+        float len = sqrtf(s);
+        v[k][0] = v[k][0] / len; v[k][1] = v[k][1] / len; v[k][2] = v[k][2] / len;
+      }
+    }
+    float d = v[0][0] * v[1][0];
+    d = d + v[0][1] * v[1][1];
+    d = d + v[0][2] * v[1][2];
+    if (fabsf(d) > eps) keep[m++] = i;
+  }
+  cloud_select(c, keep, m);
+  free(keep);
+  return ORC_OK;
+}
+
 static int filter_max_density(const orc_filter *f, orc_cloud *c) {
   /* MaxDensityDataPointsFilter [UPSTREAM-RECALLED, DataPointsFilters/MaxDensity.cpp]:
    * a point denser than maxDensity survives with probability maxDensity/density;
@@ -1172,6 +1231,10 @@ int orc_filter_apply(const orc_filter *f, orc_cloud *c) {
     case ORC_F_OBSERVATION_DIRECTION: return filter_observation_direction(f, c);
     case ORC_F_ORIENT_NORMALS: return filter_orient_normals(f, c);
     case ORC_F_SIMPLE_SENSOR_NOISE: return filter_simple_sensor_noise(f, c);
+    case ORC_F_IDENTITY: return ORC_OK;
+    case ORC_F_REMOVE_NAN: return filter_remove_nan(c);
+    case ORC_F_FIX_STEP_SAMPLING: return filter_fix_step_sampling(f, c);
+    case ORC_F_SHADOW: return filter_shadow(f, c);
     case ORC_F_MAX_DIST: return filter_dist(f, c, 1);
     case ORC_F_MIN_DIST: return filter_dist(f, c, 0);
     default: return ORC_INVALID_PARAMETER;

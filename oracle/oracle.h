@@ -89,10 +89,14 @@ enum {
   ORC_F_MIN_DIST = 8,        /* i0 = dim (-1 radial), p0 = minDist          */
   ORC_F_BOUNDING_BOX = 9,    /* box[6] = xMin,xMax,yMin,yMax,zMin,zMax; i0 = removeInside */
   ORC_F_MAX_DENSITY = 10,    /* p0 = maxDensity, i0 = seed; needs `densities` */
-  ORC_F_SAMPLING_SURFACE_NORMAL = 11 /* p0 = ratio, p1 = maxBoxDim, p2 = seed, i0 = knn,
+  ORC_F_SAMPLING_SURFACE_NORMAL = 11, /* p0 = ratio, p1 = maxBoxDim, p2 = seed, i0 = knn,
                                 i1 flags (bit0 normals, bit1 densities, bit2 eigValues,
                                 bit3 eigVectors, bit4 samplingMethod = bin,
                                 bit5 averageExistingDescriptors)              */
+  ORC_F_REMOVE_NAN = 12,      /* drops every point with a NaN coordinate      */
+  ORC_F_FIX_STEP_SAMPLING = 13, /* i0 = step, i1 = seed (phase = hash % step) */
+  ORC_F_SHADOW = 14,         /* p0 = eps; needs `normals`                    */
+  ORC_F_IDENTITY = 15
 };
 typedef struct {
   int type;

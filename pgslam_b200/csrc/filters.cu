@@ -130,6 +130,42 @@ density_keep_kernel(const float* __restrict__ dens, int* __restrict__ keep, int 
   keep[i] = k;
 }
 
+// RemoveNaN / FixStepSampling / Shadow keep flags (libpointmatcher DataPointsFilters/RemoveNaN.cpp,
+// FixStepSampling.cpp, Shadow.cpp; fp32 in the contract's x,y,z order, no FMA)
+__global__ void __launch_bounds__(256) nan_keep_kernel(const float4* __restrict__ feat, int* __restrict__ keep, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = feat[i];
+  keep[i] = !(isnan(p.x) || isnan(p.y) || isnan(p.z));
+}
+__global__ void __launch_bounds__(256) step_keep_kernel(int* __restrict__ keep, int n, int step, int phase) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = i >= phase && (i - phase) % step == 0;
+}
+__device__ __forceinline__ float3 normalized_rn(float x, float y, float z) {
+  float s = __fmul_rn(x, x);
+  s = __fadd_rn(s, __fmul_rn(y, y));
+  s = __fadd_rn(s, __fmul_rn(z, z));
+  if (s > 0.f) {
+    const float len = __fsqrt_rn(s);
+    return make_float3(__fdiv_rn(x, len), __fdiv_rn(y, len), __fdiv_rn(z, len));
+  }
+  return make_float3(x, y, z);
+}
+__global__ void __launch_bounds__(256)
+shadow_keep_kernel(const float4* __restrict__ feat, const float* __restrict__ normals, int* __restrict__ keep, int n,
+                   float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = feat[i];
+  const float3 a = normalized_rn(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+  const float3 b = normalized_rn(p.x, p.y, p.z);
+  float d = __fmul_rn(a.x, b.x);
+  d = __fadd_rn(d, __fmul_rn(a.y, b.y));
+  d = __fadd_rn(d, __fmul_rn(a.z, b.z));
+  keep[i] = fabsf(d) > eps;
+}
+
 __global__ void __launch_bounds__(256)
 dist_keep_kernel(const float4* __restrict__ feat, int* __restrict__ keep, int n, int dim, float lim, int is_max) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -786,7 +822,7 @@ void rigid_transform_cloud(Cloud& c, const double* T) {
 void apply_filter(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   cudaStream_t s = ctx->stream;
   const std::string& name = m.name;
-  if (name == "IdentityDataPointsFilter" || name == "RemoveNaNDataPointsFilter") return;
+  if (name == "IdentityDataPointsFilter") return;
   if (name == "SurfaceNormalDataPointsFilter") { surface_normals(ctx, m, clouds); return; }
   for (Cloud* cp : clouds) {
     Cloud& c = *cp;
@@ -837,6 +873,41 @@ void apply_filter(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
       box_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, keep.p, n, (float)m.real("xMin"), (float)m.real("xMax"),
                                                        (float)m.real("yMin"), (float)m.real("yMax"), (float)m.real("zMin"),
                                                        (float)m.real("zMax"), m.flag("removeInside") ? 1 : 0);
+      ctx_count_launches(ctx, 1);
+      compact_cloud(c, keep.p);
+      continue;
+    } else if (name == "RemoveNaNDataPointsFilter") {
+      if (!n) continue;
+      DBuf<int> keep(ctx, n);
+      nan_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, keep.p, n);
+      ctx_count_launches(ctx, 1);
+      compact_cloud(c, keep.p);
+      continue;
+    } else if (name == "FixStepSamplingDataPointsFilter") {
+      const int64_t step = m.integer("startStep");
+      if (m.integer("endStep") != step || m.real("stepMult") != 1.0)
+        throw Error(PGS_INVALID_PARAMETER,
+                    "FixStepSamplingDataPointsFilter: step schedules across calls (endStep != startStep or stepMult != 1) "
+                    "are not supported");
+      if (!n) continue;
+      uint64_t x = (uint64_t)m.integer("seed");
+      for (int r = 0; r < 2; ++r) {  // splitmix64 twice, as random_keep_kernel hashes its seed
+        x += 0x9E3779B97F4A7C15ull;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x = x ^ (x >> 31);
+      }
+      DBuf<int> keep(ctx, n);
+      step_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(keep.p, n, (int)step, (int)(x % (uint64_t)step));
+      ctx_count_launches(ctx, 1);
+      compact_cloud(c, keep.p);
+      continue;
+    } else if (name == "ShadowDataPointsFilter") {
+      Desc* nrm = c.find("normals");
+      if (!nrm) throw Error(PGS_INVALID_FIELD, "ShadowDataPointsFilter, Error: cannot find normals in descriptors");
+      if (!n) continue;
+      DBuf<int> keep(ctx, n);
+      shadow_keep_kernel<<<ceil_div(n, 256), 256, 0, s>>>(c.feat.p, nrm->data.p, keep.p, n, (float)m.real("eps"));
       ctx_count_launches(ctx, 1);
       compact_cloud(c, keep.p);
       continue;

@@ -28,6 +28,13 @@ const std::vector<ModuleDoc>& registry() {
       // ---- DataPointsFilters (A3-A6, A.9) --------------------------------
       {Kind::DataPointsFilter, "IdentityDataPointsFilter", {}},
       {Kind::DataPointsFilter, "RemoveNaNDataPointsFilter", {}},
+      {Kind::DataPointsFilter, "FixStepSamplingDataPointsFilter",
+       {{"startStep", "keep one point in `startStep`", "10", "1", IMAX, 'i'},
+        {"endStep", "must equal startStep (step schedules across calls are not supported)", "10", "1", IMAX, 'i'},
+        {"stepMult", "must be 1", "1", "0.0000001", INF, 'f'},
+        {"seed", "seed of the phase (upstream: rand() % step, SURVEY H7)", "0", "0", "", 'i'}}},
+      {Kind::DataPointsFilter, "ShadowDataPointsFilter",
+       {{"eps", "minimum |cos| between the normal and the ray from the origin", "0.1", "0.0000001", "3.1416", 'f'}}},
       {Kind::DataPointsFilter, "RandomSamplingDataPointsFilter",
        {{"prob", "probability to keep a point", "0.75", "0", "1", 'f'},
         {"seed", "seed of the counter-based generator (SURVEY H7)", "0", "0", "", 'i'}}},

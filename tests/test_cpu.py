@@ -523,3 +523,44 @@ def test_two_rank_gloo_sharding_gives_the_unsharded_results(tmp_path):
         want = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))
         assert np.array_equal(a[i, :16].reshape(4, 4).T, want["T"])  # independent of the sharding
         assert int(a[i, 52]) == want["iterations"]
+
+
+def test_oracle_remove_nan_fix_step_shadow():
+    """pins of the three element-wise filters against plain numpy statements of the same rules"""
+    rd, _, _ = synth.scan_pair(5, beams=16, az_steps=500)
+    # RemoveNaN
+    bad = rd.copy()
+    bad[1, ::7] = np.nan
+    c = ob.Cloud(bad)
+    assert ob.apply_filter(c, "RemoveNaNDataPointsFilter") == 0
+    keep = ~np.isnan(bad[:3]).any(axis=0)
+    assert np.array_equal(c.features, bad[:, keep])
+    # FixStep: every step-th point from a phase < step, order preserved
+    c = ob.Cloud(rd)
+    assert ob.apply_filter(c, "FixStepSamplingDataPointsFilter", startStep=9, endStep=9, seed=4) == 0
+    out = c.features
+    phases = [ph for ph in range(9) if np.array_equal(out, rd[:, ph::9])]
+    assert len(phases) == 1
+    # Shadow: |cos(normal, ray)| > eps in fp32
+    c = ob.Cloud(rd)
+    assert ob.apply_filter(c, "SurfaceNormalDataPointsFilter", knn=8) == 0
+    nrm = c.descriptors()["normals"].astype(np.float32)
+    pts = c.features[:3].astype(np.float32)
+    assert ob.apply_filter(c, "ShadowDataPointsFilter", eps=0.3) == 0
+
+    def unit(v):
+        s = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]
+        return np.where(s > 0, v / np.sqrt(np.where(s > 0, s, 1)).astype(np.float32), v).astype(np.float32)
+    a, b = unit(nrm), unit(pts)
+    cosv = np.abs((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2])
+    want = cosv > np.float32(0.3)
+    assert 0 < want.sum() < want.size
+    assert np.array_equal(c.features[:3], pts[:, want])
+    assert ob.apply_filter(ob.Cloud(rd), "ShadowDataPointsFilter") != 0  # no normals -> InvalidField
+
+
+def test_config_accepts_the_added_filters():
+    assert pm.check_config("- RemoveNaNDataPointsFilter\n- FixStepSamplingDataPointsFilter: {startStep: 5, endStep: 5}\n"
+                           "- ShadowDataPointsFilter: {eps: 0.2}\n- IdentityDataPointsFilter\n", chain=False) == 4
+    with pytest.raises(pm.InvalidParameter):
+        pm.check_config("- ShadowDataPointsFilter: {epsilon: 0.2}\n", chain=False)

@@ -161,6 +161,8 @@ def test_voxel_grid_bit_exact(pm, pair120k, centroid):
     ("MinDistDataPointsFilter", {"dim": 0, "minDist": 1.5}),
     ("BoundingBoxDataPointsFilter", {"xMin": -8, "xMax": 12, "yMin": -6, "yMax": 5, "zMin": -3, "zMax": 0.5, "removeInside": 0}),
     ("BoundingBoxDataPointsFilter", {"xMin": -8, "xMax": 12, "yMin": -6, "yMax": 5, "zMin": -3, "zMax": 0.5, "removeInside": 1}),
+    ("FixStepSamplingDataPointsFilter", {"startStep": 7, "endStep": 7, "seed": 3}),
+    ("FixStepSamplingDataPointsFilter", {}),
 ])
 def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
     rd, _, _ = pair30k
@@ -172,6 +174,50 @@ def test_subsampling_filters_bit_exact(pm, pair30k, name, params):
     assert ob.apply_filter(oc, name, **params) == 0
     assert 0 < oc.n < rd.shape[1]
     _cmp_cloud(dp, oc)
+
+
+def test_remove_nan_filter_bit_exact(pm, pair30k):
+    rd, _, _ = pair30k
+    rd = rd.copy()
+    g = np.random.default_rng(3)
+    bad = g.choice(rd.shape[1], 500, replace=False)
+    rd[g.integers(0, 3, bad.size), bad] = np.nan
+    rd[:3, bad[:20]] = np.nan  # whole points too
+    desc = {"simpleSensorNoise": np.arange(rd.shape[1], dtype=np.float32)[None]}
+    dp = pm.DataPoints(rd, desc)
+    pm.DataPointsFilters("- RemoveNaNDataPointsFilter\n").apply(dp)
+    oc = ob.Cloud(rd, desc)
+    assert ob.apply_filter(oc, "RemoveNaNDataPointsFilter") == 0
+    assert oc.n == rd.shape[1] - 500
+    _cmp_cloud(dp, oc)
+    assert not np.isnan(dp.features).any()
+    # a clean cloud passes through untouched, an Identity filter always does
+    dp2 = pm.DataPoints(pair30k[0])
+    pm.DataPointsFilters("- RemoveNaNDataPointsFilter\n- IdentityDataPointsFilter\n").apply(dp2)
+    assert np.array_equal(dp2.features, pair30k[0])
+
+
+@pytest.mark.parametrize("eps", [0.1, 0.35])
+def test_shadow_filter_bit_exact(pm, pair30k, eps):
+    rd, _, _ = pair30k
+    chain = [{"SurfaceNormalDataPointsFilter": {"knn": 8}}, {"ShadowDataPointsFilter": {"eps": eps}}]
+    dp = pm.DataPoints(rd)
+    pm.DataPointsFilters(util.to_yaml(chain)).apply(dp)
+    oc = ob.Cloud(rd)
+    for it in chain:
+        (name, p), = ob._modlist([it])
+        assert ob.apply_filter(oc, name, **p) == 0
+    assert 0 < oc.n < rd.shape[1]
+    _cmp_cloud(dp, oc)
+    # without normals: InvalidField, as upstream
+    with pytest.raises(pm.InvalidField):
+        pm.DataPointsFilters("- ShadowDataPointsFilter\n").apply(pm.DataPoints(rd))
+
+
+def test_fix_step_schedule_is_rejected(pm, pair30k):
+    with pytest.raises(pm.InvalidParameter):
+        pm.DataPointsFilters("- FixStepSamplingDataPointsFilter: {startStep: 10, endStep: 2, stepMult: 0.5}\n").apply(
+            pm.DataPoints(pair30k[0]))
 
 
 @pytest.mark.parametrize("params", [
