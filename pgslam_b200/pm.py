@@ -325,6 +325,18 @@ class DataPoints:
     def descriptors(self) -> dict:
         return {l: self.getDescriptorByName(l) for l, _ in self.descriptorLabels()}
 
+    @classmethod
+    def load(cls, path: str, ctx: "Context | None" = None) -> "DataPoints":
+        """DataPoints::load (csv / vtk / ply, by extension): host parse, one upload."""
+        from . import cloud_io as _io
+        feats, desc = _io.load(path)
+        return cls(feats, desc or None, ctx=ctx)
+
+    def save(self, path: str):
+        """DataPoints::save (csv / vtk / ply, by extension)."""
+        from . import cloud_io as _io
+        _io.save(path, self.features, self.descriptors())
+
     def copy(self) -> "DataPoints":
         h = _vp()
         self.ctx.check(self.ctx.lib.pgs_cloud_copy(self.h, C.byref(h)))

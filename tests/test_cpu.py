@@ -564,3 +564,57 @@ def test_config_accepts_the_added_filters():
                            "- ShadowDataPointsFilter: {eps: 0.2}\n- IdentityDataPointsFilter\n", chain=False) == 4
     with pytest.raises(pm.InvalidParameter):
         pm.check_config("- ShadowDataPointsFilter: {epsilon: 0.2}\n", chain=False)
+
+
+@pytest.mark.parametrize("ext", ["csv", "vtk", "ply"])
+def test_cloud_files_round_trip(tmp_path, ext):
+    """DataPoints::save / load in libpointmatcher's text formats (host-side, §8f F4)"""
+    from pgslam_b200 import cloud_io
+    g = np.random.default_rng(0)
+    n = 257
+    feats = np.vstack([g.normal(size=(3, n)).astype(np.float32) * 30, np.ones((1, n), np.float32)])
+    desc = {"normals": g.normal(size=(3, n)).astype(np.float32),
+            "simpleSensorNoise": g.random((1, n)).astype(np.float32),
+            "observationDirections": g.normal(size=(3, n)).astype(np.float32)}
+    if ext == "vtk":
+        desc["eigVectors"] = g.normal(size=(9, n)).astype(np.float32)
+    path = str(tmp_path / f"cloud.{ext}")
+    cloud_io.save(path, feats, desc)
+    f2, d2 = cloud_io.load(path)
+    assert np.array_equal(f2, feats)          # %.9g round-trips float32 exactly
+    assert set(d2) == set(desc)
+    for k in desc:
+        assert np.array_equal(d2[k], desc[k]), k
+    # empty cloud
+    cloud_io.save(path, np.zeros((4, 0), np.float32))
+    f3, d3 = cloud_io.load(path)
+    assert f3.shape == (4, 0) and d3 == {}
+
+
+def test_cloud_files_as_libpointmatcher_writes_them(tmp_path):
+    from pgslam_b200 import cloud_io
+    p = tmp_path / "a.csv"
+    p.write_text("x,y,z,nx,ny,nz,intensity\n1,2,3,0,0,1,0.5\n4,5,6,1,0,0,0.25\n")
+    f, d = cloud_io.load(str(p))
+    assert np.array_equal(f, np.array([[1, 4], [2, 5], [3, 6], [1, 1]], np.float32))
+    assert np.array_equal(d["normals"], np.array([[0, 1], [0, 0], [1, 0]], np.float32))
+    assert np.array_equal(d["intensity"], np.array([[0.5, 0.25]], np.float32))
+    p = tmp_path / "b.csv"          # no header: x y z, whitespace separated
+    p.write_text("1 2 3\n4 5 6\n")
+    f, d = cloud_io.load(str(p))
+    assert f.shape == (4, 2) and d == {} and f[2, 1] == 6
+    p = tmp_path / "c.vtk"
+    p.write_text("# vtk DataFile Version 3.0\nFile created by libpointmatcher\nASCII\nDATASET POLYDATA\n"
+                 "POINTS 2 float\n1 2 3\n4 5 6\nVERTICES 2 4\n1 0\n1 1\nPOINT_DATA 2\n"
+                 "NORMALS normals float\n0 0 1\n1 0 0\nSCALARS densities float 1\nLOOKUP_TABLE default\n7\n8\n")
+    f, d = cloud_io.load(str(p))
+    assert np.array_equal(f[:3].T, np.array([[1, 2, 3], [4, 5, 6]], np.float32))
+    assert np.array_equal(d["normals"].T, np.array([[0, 0, 1], [1, 0, 0]], np.float32))
+    assert np.array_equal(d["densities"], np.array([[7, 8]], np.float32))
+    p = tmp_path / "d.ply"
+    p.write_text("ply\nformat ascii 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property float nx\nproperty float ny\nproperty float nz\nend_header\n1 2 3 0 0 1\n4 5 6 1 0 0\n")
+    f, d = cloud_io.load(str(p))
+    assert np.array_equal(f[:3, 1], np.array([4, 5, 6], np.float32)) and d["normals"].shape == (3, 2)
+    with pytest.raises(ValueError):
+        cloud_io.load(str(tmp_path / "x.pcd"))
