@@ -56,6 +56,7 @@ struct Ctx {
   pgs_stage_times times{};
   // pinned staging + mapped progress words for the ICP loop
   void* pinned = nullptr;
+  void* pinned_dev = nullptr;  // device alias of the pinned ring (the ring is mapped)
   size_t pinned_bytes = 0, pinned_head = 0;
   volatile int* h_progress = nullptr;  // mapped host word: set to 1 by the device when no pair is active
   volatile int* d_progress = nullptr;  // device alias of h_progress

@@ -17,6 +17,7 @@
 // to stop launching once every pair has converged.
 #include "icp.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <thread>
@@ -1382,15 +1383,28 @@ void IcpEngine::run_batch(const std::vector<const Cloud*>& readings, const std::
       if (!e) PGS_CUDA(cudaEventCreate(&e));
     PGS_CUDA(cudaEventRecord(idx_ev_[0], ctx_->stream));
   }
+  // PGS_TRACE_STALL=<ms>: report the host-side phases of any (sub-)batch slower than that
+  static const double stall_ms = std::getenv("PGS_TRACE_STALL") ? std::atof(std::getenv("PGS_TRACE_STALL")) : 0.0;
+  const auto now = [] { return std::chrono::steady_clock::now(); };
+  const auto t0 = now();
   std::vector<std::unique_ptr<Cloud>> refs(P);
   for (int p = 0; p < P; ++p) refs[p] = references[p]->clone(ctx_);
+  const auto t1 = now();
   std::vector<std::unique_ptr<PreparedRef>> prepared;
   prepare_references(refs, false, prepared);
+  const auto t2 = now();
   if (ctx_->profiling) PGS_CUDA(cudaEventRecord(idx_ev_[1], ctx_->stream));
   have_idx_ev_ = ctx_->profiling;
   std::vector<const PreparedRef*> rp(P);
   for (int p = 0; p < P; ++p) rp[p] = prepared[p].get();
   run_prepared(readings, rp, T_inits, results);
+  const auto t3 = now();
+  if (stall_ms > 0.0) {
+    const auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    if (ms(t0, t3) > stall_ms)
+      std::fprintf(stderr, "[pgs] slow batch of %d on stream %p: clone %.1f ms, prepare_references %.1f ms, run_prepared %.1f ms\n",
+                   P, (void*)ctx_->stream, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
 }
 
 void IcpEngine::set_map(const Cloud& map) {

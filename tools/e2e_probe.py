@@ -21,7 +21,8 @@ for mode in ('sync-upload', 'pipelined'):
     pending = [upload()]
     torch.cuda.synchronize()
     t_all = time.perf_counter()
-    for step in range(8):
+    per = []
+    for step in range(int(sys.argv[3]) if len(sys.argv) > 3 else 8):
         t0 = time.perf_counter()
         if mode == 'pipelined':
             cur = pending.pop(); pending.append(upload())
@@ -32,8 +33,11 @@ for mode in ('sync-upload', 'pipelined'):
         t2 = time.perf_counter()
         del cur
         tu += t1 - t0; tc += t2 - t1
+        t3 = time.perf_counter()
+        per.append((round(1e3*(t1-t0),1), round(1e3*(t2-t1),1), round(1e3*(t3-t2),1)))
     torch.cuda.synchronize()
     tot = time.perf_counter() - t_all
+    print('per step (upload-call, compute-call, del):', per)
     print(mode, 'per step ms: upload-call %.2f compute-call %.2f total %.2f -> %.0f reg/s' % (1e3*tu/8, 1e3*tc/8, 1e3*tot/8, B*8/tot))
 # resident for comparison
 rds, rfs = upload(); torch.cuda.synchronize()
