@@ -472,14 +472,12 @@ void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   std::vector<std::shared_ptr<Index>> idx;
   cached_indices_for_clouds(ctx, clouds, idx);
   std::vector<DBuf<int32_t>> ids(B);
-  std::vector<DBuf<float>> d2(B);
   std::vector<const Index*> ip(B);
   std::vector<int32_t*> idp(B);
-  std::vector<float*> d2p(B);
+  std::vector<float*> d2p(B, nullptr);  // the covariance only needs WHICH points: no distances written
   for (int b = 0; b < B; ++b) {
     ids[b].reset(ctx, (size_t)std::max(ns[b], 1) * k);
-    d2[b].reset(ctx, (size_t)std::max(ns[b], 1) * k);
-    ip[b] = idx[b].get(); idp[b] = ids[b].p; d2p[b] = d2[b].p;
+    ip[b] = idx[b].get(); idp[b] = ids[b].p;
   }
   knn_self_batched(ctx, ip, k, max_dist, idp, d2p);
   std::vector<NormalJob> jobs(B);

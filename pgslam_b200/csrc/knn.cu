@@ -65,7 +65,7 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
     if (e < k) {
       const int id = key_id(acc.key[e]);
       oi[e] = (id == 0x7fffffff) ? -1 : id;
-      od[e] = (id == 0x7fffffff) ? __int_as_float(0x7f800000) : key_dist(acc.key[e]);
+      if (job.d2) od[e] = (id == 0x7fffffff) ? __int_as_float(0x7f800000) : key_dist(acc.key[e]);
     }
   }
 }
