@@ -49,6 +49,10 @@ __host__ __device__ inline int reduce_slices(int n, int per_block, int max_block
 }
 constexpr int kAccPerBlock = 4096;
 constexpr int kAccMaxBlocks = 128;
+#ifndef PGS_ACC_UNROLL
+#define PGS_ACC_UNROLL 4
+#endif
+constexpr int kAccUnroll = PGS_ACC_UNROLL;  // matches whose loads are in flight together in accumulate_kernel
 
 // ---------------------------------------------------------------------------
 // per-pair accumulation of one weighted match (A.5 / A.7), all in fp64
@@ -426,15 +430,17 @@ gather_vec3_sorted_kernel(const float4* __restrict__ sorted_pts, int n, const fl
 struct GatherJob {
   const float4* sorted_pts;
   const float* src;
-  float4* out4;
+  float4* out4;  // 2 float4 per sorted position: {point, normal} = one 32-byte sector per match
   int n;
 };
 __global__ void __launch_bounds__(256) gather_vec3_sorted_batched_kernel(const GatherJob* __restrict__ jobs) {
   const GatherJob job = jobs[blockIdx.y];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= job.n) return;
-  const int o = __float_as_int(job.sorted_pts[j].w);
-  job.out4[j] = make_float4(job.src[3 * o], job.src[3 * o + 1], job.src[3 * o + 2], 0.f);
+  const float4 p = job.sorted_pts[j];
+  const int o = __float_as_int(p.w);
+  job.out4[2 * j] = p;
+  job.out4[2 * j + 1] = make_float4(job.src[3 * o], job.src[3 * o + 1], job.src[3 * o + 2], 0.f);
 }
 
 constexpr int kSeedLevels = 10;  // levels above the seed leaf searched top-down (a 2^10-leaf neighbourhood)
@@ -770,7 +776,10 @@ __global__ void fixed_limits_kernel(PairState* __restrict__ states, IcpParams P,
   states[p].lim_lo = P.fixed_lo;
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef PGS_ACC_MIN_BLOCKS
+#define PGS_ACC_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, PGS_ACC_MIN_BLOCKS)
 accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int* n_active,
                   volatile int* h_done) {
   __shared__ double sh[8][kAcc];
@@ -783,32 +792,59 @@ accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ st
   if (blockIdx.x >= slices) return;
   const Xf T = st.xf;
   const float lo = st.lim_lo, hi = st.lim_hi;
+  // The kernel holds 30 fp64 accumulators (128 registers, 2 blocks / SM), so there are few warps
+  // to hide the three dependent DRAM latencies of a match (position + distance -> reading point
+  // -> matched record): with one match at a time they were the whole run time (ncu: long
+  // scoreboard on the first use of every load, issue slots 24 % busy).  kAccUnroll matches are
+  // therefore loaded together - their streaming loads first, then an L2 prefetch of each matched
+  // record - before any arithmetic; the matches are still accumulated in the same order.
+  const float4* __restrict__ rec = v.ref_normals ? v.ref_normals : v.tree.pts;
+  const int rstride = v.ref_normals ? 2 : 1;
+  const int stride = (int)slices * blockDim.x;
   double acc[kAcc];
 #pragma unroll
   for (int j = 0; j < kAcc; ++j) acc[j] = 0.0;
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < v.n_m; m += slices * blockDim.x) {
-    const int i = P.knn == 1 ? m : m / P.knn;
-    const int pos = v.match_pos[m];
-    const float d = v.match_d2[m];
-    // ErrorElements skips dist == inf; OutlierFilters weights are 0/1 here
-    bool use = pos >= 0 && d < kInfF;
-    if (P.has_outliers) use = use && d <= hi && d >= lo;
-    if (!use) continue;
-    if (P.has_sn && v.rd_normals && v.ref_normals) {
-      float4 a = v.rd_normals[i];
-      float3 ar = rot_rn(T, a.x, a.y, a.z);
-      float4 b = v.ref_normals[pos];
-      if (sn_reject(ar.x, ar.y, ar.z, b.x, b.y, b.z, P.sn_eps)) continue;
+  for (int m0 = blockIdx.x * blockDim.x + threadIdx.x; m0 < v.n_m; m0 += kAccUnroll * stride) {
+    int pos[kAccUnroll];
+    float4 r[kAccUnroll];
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      const int m = m0 + u * stride;
+      pos[u] = -1;
+      r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < v.n_m) {
+        const int pp = v.match_pos[m];
+        const float d = v.match_d2[m];
+        r[u] = v.reading[P.knn == 1 ? m : m / P.knn];
+        // ErrorElements skips dist == inf; OutlierFilters weights are 0/1 here
+        bool use = pp >= 0 && d < kInfF;
+        if (P.has_outliers) use = use && d <= hi && d >= lo;
+        pos[u] = use ? pp : -1;
+      }
     }
-    float4 r = v.reading[i];
-    float3 p = xform_rn(T, r.x, r.y, r.z);
-    float4 q = v.tree.pts[pos];
-    float3 n = make_float3(0.f, 0.f, 0.f);
-    if (P.minimizer != MIN_P2POINT) {
-      float4 n4 = v.ref_normals[pos];
-      n = make_float3(n4.x, n4.y, n4.z);
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u)
+      if (pos[u] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (size_t)rstride * pos[u]));
+#pragma unroll
+    for (int u = 0; u < kAccUnroll; ++u) {
+      if (pos[u] < 0) continue;
+      if (P.has_sn && v.rd_normals && v.ref_normals) {
+        const int m = m0 + u * stride;
+        float4 a = v.rd_normals[P.knn == 1 ? m : m / P.knn];
+        float3 ar = rot_rn(T, a.x, a.y, a.z);
+        float4 b = v.ref_normals[2 * pos[u] + 1];
+        if (sn_reject(ar.x, ar.y, ar.z, b.x, b.y, b.z, P.sn_eps)) continue;
+      }
+      float3 p = xform_rn(T, r[u].x, r[u].y, r[u].z);
+      // matched point and its normal sit in one 32-byte record when the reference has normals
+      float4 q = rec[(size_t)rstride * pos[u]];
+      float3 n = make_float3(0.f, 0.f, 0.f);
+      if (P.minimizer != MIN_P2POINT) {
+        float4 n4 = v.ref_normals[2 * pos[u] + 1];
+        n = make_float3(n4.x, n4.y, n4.z);
+      }
+      accumulate_match(acc, P.minimizer, p, q, n, 1.0, P.force_mode);
     }
-    accumulate_match(acc, P.minimizer, p, q, n, 1.0, P.force_mode);
   }
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -878,14 +914,14 @@ final_accumulate_kernel(const PairView* __restrict__ views, PairState* __restric
     if (P.has_sn && v.rd_normals && v.ref_normals) {
       float4 a = v.rd_normals[i];
       float3 ar = rot_rn(T, a.x, a.y, a.z);
-      float4 b = v.ref_normals[pos];
+      float4 b = v.ref_normals[2 * pos + 1];
       if (sn_reject(ar.x, ar.y, ar.z, b.x, b.y, b.z, P.sn_eps)) continue;
     }
     float4 r = v.reading[i];
     float3 p = xform_rn(T, r.x, r.y, r.z);
     float4 q = v.tree.pts[pos];
     if (want_cov) {
-      float4 n4 = v.ref_normals[pos];
+      float4 n4 = v.ref_normals[2 * pos + 1];
       accumulate_cov(acc, p, q, make_float3(n4.x, n4.y, n4.z), alpha, beta, gamma, t);
     }
     if (want_overlap) {
@@ -1307,7 +1343,7 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     const Desc* nrm = rp[b]->find("normals");
     pr->has_normals = nrm != nullptr;
     if (nrm && ns[b] > 0) {
-      pr->normals_sorted.reset(ctx, (size_t)ns[b]);
+      pr->normals_sorted.reset(ctx, (size_t)2 * ns[b]);
       gjobs.push_back(GatherJob{pr->index->pts.p, nrm->data.p, pr->normals_sorted.p, ns[b]});
       gmax = std::max(gmax, ns[b]);
     }

@@ -76,7 +76,7 @@ struct PairView {
   int n_m;                     // matches = knn * n_r, stored [point][neighbour] like PM's k x N Matches
   const int* ref_inv;          // original reference index -> sorted position (knn > 1 only)
   TreeView tree;               // reference index
-  const float4* ref_normals;   // per sorted reference position, or null
+  const float4* ref_normals;   // {point, normal} per sorted reference position (2 float4), or null
   const float4* rd_normals;    // per sorted reading position (pre-transformed), or null
   const float* rd_noise;       // per sorted reading position, or null
   int* match_pos;
