@@ -545,20 +545,26 @@ select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ s
   const unsigned mask = pass == 0 ? 0u : st.sel_mask;
   for (int d = tid; d < kSelBins; d += 256) hist[d] = 0;
   __syncthreads();
-  for (int base = blockIdx.x * 256; base < v.n_m; base += gridDim.x * 256) {
-    const int i = base + tid;
-    unsigned u = 0;
-    bool valid = false;
-    if (i < v.n_m) {
-      u = __float_as_uint(v.match_d2[i]);
-      // getDistsQuantile: dist != inf and dist > 0
-      valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
+  // four tiles per trip: their loads are issued together (the kernel is one wave of blocks
+  // waiting on DRAM, not on arithmetic)
+  for (int base = blockIdx.x * 256; base < v.n_m; base += gridDim.x * 256 * 4) {
+    unsigned uu[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = base + r * (int)gridDim.x * 256 + tid;
+      uu[r] = i < v.n_m ? __float_as_uint(v.match_d2[i]) : 0u;
     }
-    unsigned act = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      unsigned d = (u >> shift) & dmask;
-      unsigned m = __match_any_sync(act, d);
-      if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned u = uu[r];
+      // getDistsQuantile: dist != inf and dist > 0 (an out-of-range slot reads as 0)
+      const bool valid = (u != 0u) && (u < 0x7f800000u) && ((u & mask) == prefix);
+      unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        unsigned d = (u >> shift) & dmask;
+        unsigned m = __match_any_sync(act, d);
+        if (lane == __ffs(m) - 1) atomicAdd(&hist[d], (unsigned)__popc(m));
+      }
     }
   }
   __syncthreads();
