@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -229,9 +229,13 @@ def main():
         loc = torch.tensor(np.stack([r["T"].ravel(order="F") for r in results]), dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(gathered, loc)
 
+    resident_wall = []  # host wall-clock of every device-resident step (warm-up included)
+
     def step_resident():
+        t0 = time.perf_counter()
         res = icp.compute_batch(dev_rd, dev_rf)
         gather(res)
+        resident_wall.append(round(1e3 * (time.perf_counter() - t0), 2))
         return res
 
     def upload():
@@ -253,10 +257,14 @@ def main():
         # inputs and downloads its own results
         t0 = time.perf_counter()
         rds, rfs = pending.pop().result() if pending else upload()
+        t1 = time.perf_counter()
         pending.append(uploader.submit(upload))
         res = icp.compute_batch(rds, rfs)
         gather(res)
         e2e_wall.append(round(1e3 * (time.perf_counter() - t0), 2))
+        if os.environ.get("BENCH_TRACE_E2E"):
+            sys.stderr.write("e2e step: waited %.1f ms for the upload calls, compute_batch %.1f ms\n"
+                             % (1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
         return res
 
     def barrier():
@@ -291,7 +299,7 @@ def main():
     # clocks are sampled from the warm-up steps on (same load as the timed steps): the
     # timed region alone is ~100 ms, too short for more than a sample or two
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(args.warmup):
         step_resident()
@@ -380,6 +388,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": int(total_pairs * 480), "ms_per_step": ms_e2e / args.steps,
                     "wall_ms_each_step_incl_warmup": e2e_wall},
+            "resident_wall_ms_each_step_incl_warmup": resident_wall[:args.warmup + args.steps],
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "knn_queries_per_s": knn_qps, "iterations_mean": statistics.mean(iters), "pairs_ok": ok,
             "single_pair_latency_ms": ms_one / 10.0}

@@ -61,6 +61,7 @@ Ctx* Ctx::worker(int i) {
     w->device = device;
     w->num_sms = num_sms;
     w->batch_streams = 1;
+    w->blocking_waits = true;
     PGS_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     w->own_stream = true;
     workers.push_back(w);
@@ -82,6 +83,7 @@ void Ctx::destroy_resources() {
   for (auto& e : copy_ev)
     if (e) cudaEventDestroy(e);
   if (fork_ev) cudaEventDestroy(fork_ev);
+  if (sync_ev) cudaEventDestroy(sync_ev);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream) cudaStreamDestroy(stream);
   pinned = nullptr;
@@ -97,7 +99,8 @@ void Ctx::ensure_progress() {
   h_progress = static_cast<volatile int*>(h);
   d_progress = static_cast<volatile int*>(d);
   *h_progress = 0;
-  for (auto& e : loop_ev) PGS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : loop_ev)
+    PGS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (blocking_waits ? cudaEventBlockingSync : 0)));
 }
 
 Desc& Cloud::add(const std::string& label, int span) {

@@ -77,7 +77,18 @@ struct Ctx {
   void* alloc(size_t bytes);
   void free(void* p);
   void upload_small(void* dst, const void* src, size_t bytes);
-  void sync() { PGS_CUDA(cudaStreamSynchronize(stream)); }
+  // Worker contexts of a batch sleep in their waits instead of spinning: a box that runs one
+  // rank per GPU has 8 x (4 workers + main + uploader) host threads on far fewer cores, and a
+  // spinning waiter that loses its core finds out late that the device went idle.  The
+  // single-registration path keeps the spinning waits (lowest latency).
+  bool blocking_waits = false;
+  cudaEvent_t sync_ev = nullptr;
+  void sync() {
+    if (!blocking_waits) { PGS_CUDA(cudaStreamSynchronize(stream)); return; }
+    if (!sync_ev) PGS_CUDA(cudaEventCreateWithFlags(&sync_ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    PGS_CUDA(cudaEventRecord(sync_ev, stream));
+    PGS_CUDA(cudaEventSynchronize(sync_ev));
+  }
 };
 
 static inline void ctx_count_launches(Ctx* ctx, int n) { ctx->launches += (uint64_t)n; }
