@@ -86,7 +86,7 @@ bool radix_sort_pairs(Ctx* ctx, K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t
 void exclusive_scan_int(Ctx* ctx, const int* d_in, int* d_out, int n, int* d_total);
 
 // ---------------------------------------------------------------------------
-// spatial index: points sorted by 30-bit Morton code, cut into leaves of kLeaf
+// spatial index: points in balanced kd-tree order (kdorder.cu), cut into leaves of kLeaf
 // consecutive points, under an implicit complete binary tree of AABBs
 // (1-based heap numbering: children of i are 2i, 2i+1; leaf j is node P+j).
 // ---------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 // knn.cu — batched exact kNN kernels (generic k) on top of knn.cuh.
-// One thread per query; queries arrive in Morton order so the lanes of a warp
-// walk nearly the same nodes (broadcast loads, little divergence).
+// One thread per query; a self-search takes its queries in tree order, so the lanes of a
+// warp share leaves and walk nearly the same nodes (broadcast loads, less divergence).
 //
 // k is a template parameter (the candidate list lives in registers); a request
 // for k neighbours runs the smallest instantiated K >= k and reports the first
@@ -11,9 +11,7 @@ namespace pgs {
 
 namespace {
 
-#ifndef PGS_SELF_GROUP
-#define PGS_SELF_GROUP 1
-#endif
+constexpr int kSelfGroup = 1;  // self-search seed: the aligned pair of leaves (16 points) around the query
 
 struct KnnJobDev {
   TreeView tree;
@@ -22,7 +20,7 @@ struct KnnJobDev {
   int nq;
   int32_t* ids;
   float* d2;
-  int self;  // queries ARE tree.pts (self-kNN): seed from the Morton neighbourhood
+  int self;  // queries ARE tree.pts (self-kNN): seed from the query's own leaf group
 };
 
 template <int K>
@@ -34,18 +32,17 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   const float4 q = job.queries[j];
   BestK<K> acc;
   acc.init(maxr2);
-  if (job.self && K <= kSeedSlots && PGS_SELF_GROUP >= 0) {
+  if (job.self && K <= kSeedSlots) {
     // the lanes that share a group of leaves share its candidates: sort them once per lane
     // without a branch, then climb from above the group on a path those lanes have in common
     if constexpr (K <= kSeedSlots) {
-      knn_seed_group<K>(job.tree, j / kLeaf, PGS_SELF_GROUP, q.x, q.y, q.z, maxr2, acc);
-      knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, acc, 0, -1, PGS_SELF_GROUP, false);
+      knn_seed_group<K>(job.tree, j / kLeaf, kSelfGroup, q.x, q.y, q.z, maxr2, acc);
+      knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, acc, 0, -1, kSelfGroup, false);
     }
-  } else
-  if (job.self) {
-    // neighbours in Morton order are mostly neighbours in space: they give a
-    // tight k-th distance before the tree is touched, so the climb from the
-    // query's own leaf enters almost no sibling subtree
+  } else if (job.self) {
+    // K > 16: neighbours in tree order are mostly neighbours in space: offering the +-K
+    // window first gives a tight k-th distance before the tree is touched, so the climb
+    // from the query's own leaf enters few sibling subtrees
     const int skip_lo = max(0, j - K), skip_hi = min(job.tree.n - 1, j + K);
     for (int p = skip_lo; p <= skip_hi; ++p) {
       float4 c = job.tree.pts[p];

@@ -38,7 +38,7 @@ for mode in ('sync-upload', 'pipelined'):
     torch.cuda.synchronize()
     tot = time.perf_counter() - t_all
     print('per step (upload-call, compute-call, del):', per)
-    print(mode, 'per step ms: upload-call %.2f compute-call %.2f total %.2f -> %.0f reg/s' % (1e3*tu/8, 1e3*tc/8, 1e3*tot/8, B*8/tot))
+    print(mode, 'per step ms: upload-call %.2f compute-call %.2f total %.2f -> %.0f reg/s' % (1e3*tu/len(per), 1e3*tc/len(per), 1e3*tot/len(per), B*len(per)/tot))
 # resident for comparison
 rds, rfs = upload(); torch.cuda.synchronize()
 t0 = time.perf_counter()
