@@ -765,6 +765,36 @@ def test_two_host_threads_two_contexts(pm):
         assert np.array_equal(out[i][0], serial[i][0])
 
 
+def test_pinned_uploads_from_a_second_thread_while_a_batch_runs(pm):
+    """The end-to-end pipeline of bench.py: the next batch is uploaded from pinned host memory
+    (pgs_cloud_create mode 2, side stream) by a helper thread while the current batch computes on
+    the same context; results must equal those of plain synchronous uploads, batch after batch."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    ctx = pm.Context(0)
+    icp = pm.ICP(ctx)
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    pairs = [synth.scan_pair(60 + s, beams=16, az_steps=600)[:2] for s in range(8)]
+    want = icp.compute_batch([pm.DataPoints(rd, ctx=ctx) for rd, _ in pairs], [pm.DataPoints(rf, ctx=ctx) for _, rf in pairs])
+    host = [(torch.from_numpy(np.ascontiguousarray(rd.T)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rf.T)).pin_memory())
+            for rd, rf in pairs]
+
+    def upload():
+        return ([pm.DataPoints(ctx=ctx, pinned_host_ptr=a.data_ptr(), n=a.shape[0]) for a, _ in host],
+                [pm.DataPoints(ctx=ctx, pinned_host_ptr=b.data_ptr(), n=b.shape[0]) for _, b in host])
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(upload)
+        for _ in range(6):
+            rds, rfs = nxt.result()
+            nxt = pool.submit(upload)
+            got = icp.compute_batch(rds, rfs)
+            for g, w in zip(got, want):
+                assert g["status"] == 0 and g["iterations"] == w["iterations"]
+                assert np.array_equal(g["T"], w["T"])
+        nxt.result()
+
+
 # ------------------------------------------------ SurfaceNormalOutlierFilter (breadth row F4) ---
 def test_surface_normal_outlier_filter_module_and_fused(pm, pair30k):
     rd, rf, _ = pair30k
