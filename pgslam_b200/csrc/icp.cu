@@ -493,9 +493,17 @@ match_k_kernel(const PairView* __restrict__ views, PairState* __restrict__ state
   float3 q = xform_rn(T, r.x, r.y, r.z);
   BestK<K> acc;
   acc.init(maxr2);
+  // same seeded search as match_kernel, from the previous NEAREST match
   const int pp = st.iterations > 0 ? v.match_pos[(size_t)i * k] : -1;
-  if (pp >= 0) knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc);
-  else knn_traverse(v.tree, q.x, q.y, q.z, acc);
+  if (pp >= 0) {
+    const float4 c = __ldg(v.tree.pts + pp);
+    acc.offer(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pp);
+    const int h = min(kSeedLevels, v.tree.depth);
+    knn_traverse_from(v.tree, (unsigned)(v.tree.P + pp / kLeaf) >> h, v.tree.depth - h, q.x, q.y, q.z, acc, pp, pp);
+    knn_climb(v.tree, pp / kLeaf, q.x, q.y, q.z, acc, pp, pp, h, false);
+  } else {
+    knn_traverse(v.tree, q.x, q.y, q.z, acc);
+  }
   int* op = v.match_pos + (size_t)i * k;
   float* od = v.match_d2 + (size_t)i * k;
 #pragma unroll
