@@ -618,3 +618,28 @@ def test_cloud_files_as_libpointmatcher_writes_them(tmp_path):
     assert np.array_equal(f[:3, 1], np.array([4, 5, 6], np.float32)) and d["normals"].shape == (3, 2)
     with pytest.raises(ValueError):
         cloud_io.load(str(tmp_path / "x.pcd"))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on
+    stdout with the contract's keys; the GPU arm refuses to run without a device instead of falling back."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "icp_registrations_per_s_120k_pt_pairs"
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and "workload" in d["config"]
+    import torch
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                              timeout=600)
+        assert ours.returncode != 0 and "no CUDA device" in (ours.stderr + ours.stdout)
