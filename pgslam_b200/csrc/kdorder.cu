@@ -116,6 +116,209 @@ kd_key_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ v
   keys[o] = (uint32_t)max(0, min((int)key_max, q));
 }
 
+// ---- global levels as a median SPLIT (radix select + stable partition) ----------------
+//
+// A level only has to put the smaller half of every segment first; both halves are re-split
+// along their own axis one level down, so sorting them is wasted work.  Per level:
+//   kd_hist     11-bit key of every point along the segment's widest axis (kept for the next
+//               two kernels) -> per-block shared-memory histogram -> merged into the segment's
+//               2048-bin histogram; the last block of a segment to finish finds the bin that
+//               holds the median and how many of its members still go left;
+//   kd_part_count   per tile: how many keys are below / in the median bin;
+//   kd_part_scatter exclusive prefix over the tiles before it, warp-ballot ranks inside the
+//               tile -> every index moves to its slot.  Stable, so the order is deterministic.
+// Points inside the median's bin are split by position: sibling boxes may overlap by 1/2047th
+// of the segment's extent (3 cm of a 60 m scene at the top level).
+constexpr int kSplitBins = 2048;
+constexpr int kSplitTile = 2048;  // elements per block: 256 threads x 8
+
+struct SplitMeta {
+  int med_bin;  // keys < med_bin go left; kSplitBins = every point goes left
+  int n_less;   // points with key < med_bin
+  int n_eq;     // points with key == med_bin
+  int tie;      // how many of those still go left
+};
+
+__global__ void __launch_bounds__(256)
+kd_hist_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ vals, int span, int segs, int S,
+               const unsigned* __restrict__ bbox, unsigned short* __restrict__ keys, unsigned* __restrict__ hist,
+               unsigned* __restrict__ tickets, SplitMeta* __restrict__ meta) {
+  __shared__ unsigned sh[kSplitBins];
+  __shared__ unsigned scan[256];
+  __shared__ bool last;
+  const int j = blockIdx.y;
+  const int b = j / segs, s = j % segs;
+  const KdCloud c = clouds[b];
+  const int cnt = seg_count(c.n, s, S);
+  if (cnt == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int d = tid; d < kSplitBins; d += 256) sh[d] = 0;
+  __syncthreads();
+  const unsigned* bb = bbox + 6 * j;
+  const int axis = widest_axis(bb);
+  const float lo = ord2f(bb[axis]), hi = ord2f(bb[3 + axis]);
+  const float scale = hi > lo ? (float)(kSplitBins - 1) / (hi - lo) : 0.f;
+  const size_t base = (size_t)j * S;
+  const int t0 = blockIdx.x * kSplitTile;
+#pragma unroll
+  for (int r = 0; r < kSplitTile / 256; ++r) {
+    const int i = t0 + r * 256 + tid;
+    const bool valid = i < cnt;
+    unsigned key = 0;
+    if (valid) {
+      const float4 p = c.pts[vals[base + i]];
+      const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+      key = (unsigned)max(0, min(kSplitBins - 1, (int)((x - lo) * scale)));
+      keys[base + i] = (unsigned short)key;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned m = __match_any_sync(act, key);
+      if (lane == __ffs(m) - 1) atomicAdd(&sh[key], (unsigned)__popc(m));
+    }
+  }
+  __syncthreads();
+  unsigned* gh = hist + (size_t)j * kSplitBins;
+  for (int d = tid; d < kSplitBins; d += 256)
+    if (sh[d]) atomicAdd(&gh[d], sh[d]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(&tickets[j], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the last block owns the segment's merged histogram
+  const int target = S / 2;  // the left child takes the first S/2 slots
+  unsigned mine[kSplitBins / 256], sum = 0;
+#pragma unroll
+  for (int u = 0; u < kSplitBins / 256; ++u) {
+    mine[u] = __ldcg(&gh[tid * (kSplitBins / 256) + u]);
+    sum += mine[u];
+  }
+  scan[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {  // inclusive scan of the 256 partial sums
+    const unsigned v = tid >= o ? scan[tid - o] : 0u;
+    __syncthreads();
+    scan[tid] += v;
+    __syncthreads();
+  }
+  if (tid == 0) tickets[j] = 0;
+  if (cnt <= target) {
+    if (tid == 0) meta[j] = SplitMeta{kSplitBins, cnt, 0, 0};
+    return;
+  }
+  const unsigned incl = scan[tid], excl = incl - sum;
+  if (excl < (unsigned)target && incl >= (unsigned)target) {  // exactly one thread
+    unsigned cum = excl;
+    int u = 0;
+    for (; u < kSplitBins / 256 - 1; ++u) {
+      if (cum + mine[u] >= (unsigned)target) break;
+      cum += mine[u];
+    }
+    meta[j] = SplitMeta{tid * (kSplitBins / 256) + u, (int)cum, (int)mine[u], target - (int)cum};
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kd_part_count_kernel(const KdCloud* __restrict__ clouds, int segs, int S, const unsigned short* __restrict__ keys,
+                     const SplitMeta* __restrict__ meta, int2* __restrict__ counts, int ntiles) {
+  __shared__ int wl[8], we[8];
+  const int j = blockIdx.y;
+  const int cnt = seg_count(clouds[j / segs].n, j % segs, S);
+  if (cnt == 0) return;
+  const int med = meta[j].med_bin;
+  const size_t base = (size_t)j * S;
+  const int t0 = blockIdx.x * kSplitTile;
+  int nl = 0, ne = 0;
+#pragma unroll
+  for (int r = 0; r < kSplitTile / 256; ++r) {
+    const int i = t0 + r * 256 + threadIdx.x;
+    if (i < cnt) {
+      const int k = keys[base + i];
+      nl += k < med;
+      ne += k == med;
+    }
+  }
+  nl = __reduce_add_sync(0xffffffffu, nl);
+  ne = __reduce_add_sync(0xffffffffu, ne);
+  if ((threadIdx.x & 31) == 0) { wl[threadIdx.x >> 5] = nl; we[threadIdx.x >> 5] = ne; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int a = 0, e = 0;
+    for (int w = 0; w < 8; ++w) { a += wl[w]; e += we[w]; }
+    counts[(size_t)j * ntiles + blockIdx.x] = make_int2(a, e);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kd_part_scatter_kernel(const KdCloud* __restrict__ clouds, int segs, int S, const uint32_t* __restrict__ vals_in,
+                       uint32_t* __restrict__ vals_out, const unsigned short* __restrict__ keys,
+                       const SplitMeta* __restrict__ meta, const int2* __restrict__ counts, int ntiles) {
+  __shared__ int wl[8], we[8];
+  __shared__ int tile_l, tile_e;
+  const int j = blockIdx.y;
+  const int cnt = seg_count(clouds[j / segs].n, j % segs, S);
+  if (cnt == 0) return;
+  const SplitMeta mt = meta[j];
+  const size_t base = (size_t)j * S;
+  const int t0 = blockIdx.x * kSplitTile;
+  if (t0 >= cnt) return;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  if (tid < 32) {  // points below / in the median bin in the tiles before this one
+    int a = 0, e = 0;
+    for (int t = lane; t < (int)blockIdx.x; t += 32) {
+      const int2 c2 = counts[(size_t)j * ntiles + t];
+      a += c2.x;
+      e += c2.y;
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    e = __reduce_add_sync(0xffffffffu, e);
+    if (lane == 0) { tile_l = a; tile_e = e; }
+  }
+  // a warp owns 256 consecutive slots of the tile (8 rounds of 32): ranks follow the slot order
+  const int w0 = t0 + w * 256;
+  int side[8], rank[8];  // rank among the warp's own less / equal / greater slots
+  uint32_t val[8];
+  int run_l = 0, run_e = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = w0 + r * 32 + lane;
+    const bool valid = i < cnt;
+    const int key = valid ? (int)keys[base + i] : 0x7fffffff;
+    val[r] = valid ? vals_in[base + i] : 0u;
+    side[r] = !valid ? 3 : (key < mt.med_bin ? 0 : (key == mt.med_bin ? 1 : 2));
+    const unsigned bl = __ballot_sync(0xffffffffu, side[r] == 0);
+    const unsigned be = __ballot_sync(0xffffffffu, side[r] == 1);
+    const unsigned lt = (1u << lane) - 1u;
+    const int less_before = run_l + __popc(bl & lt), eq_before = run_e + __popc(be & lt);
+    // valid slots are contiguous from the start of the segment, so every slot before a valid one is valid
+    rank[r] = side[r] == 0 ? less_before : (side[r] == 1 ? eq_before : r * 32 + lane - less_before - eq_before);
+    run_l += __popc(bl);
+    run_e += __popc(be);
+  }
+  if (lane == 0) { wl[w] = run_l; we[w] = run_e; }
+  __syncthreads();
+  int off_l = tile_l, off_e = tile_e;  // less / equal points of the segment before this warp's slots
+  for (int q = 0; q < w; ++q) { off_l += wl[q]; off_e += we[q]; }
+  const int half = S / 2;
+  const int off_g = w0 - off_l - off_e;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (side[r] == 3) continue;
+    int dst;
+    if (side[r] == 0) {
+      dst = off_l + rank[r];
+    } else if (side[r] == 1) {
+      const int e = off_e + rank[r];
+      dst = e < mt.tie ? mt.n_less + e : half + (e - mt.tie);
+    } else {
+      dst = half + (mt.n_eq - mt.tie) + off_g + rank[r];
+    }
+    vals_out[base + dst] = val[r];
+  }
+}
+
 // ---- local levels: one block owns m0 (<= kLocal) consecutive slots ------------
 //
 // Sub-segments of kRadixMin points or more are SPLIT, not sorted: only the median
@@ -383,7 +586,26 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
   uint32_t* other = vals_b.p;
   kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, cur, span);
   ctx_count_launches(ctx, 1);
+  // PGS_KD_SPLIT_LEVELS=1 selects the median-split global levels (not yet validated on the GPU:
+  // the default stays the segmented radix sorts every measurement in DESIGN.md was taken with)
+  static const bool sort_levels = !(std::getenv("PGS_KD_SPLIT_LEVELS") && std::atoi(std::getenv("PGS_KD_SPLIT_LEVELS")) != 0);
   int level = 0;
+  int n_levels = 0;
+  while ((span >> n_levels) > kLocal) ++n_levels;
+  const int max_jobs = n_levels > 0 ? B << (n_levels - 1) : 0;
+  const int max_tiles = ceil_div(std::min(span, max_n), kSplitTile);
+  DBuf<unsigned> hist;
+  DBuf<unsigned> tickets;
+  DBuf<SplitMeta> meta;
+  DBuf<int2> counts;
+  if (!sort_levels && n_levels > 0) {
+    hist.reset(ctx, (size_t)max_jobs * kSplitBins);
+    tickets.reset(ctx, (size_t)max_jobs);
+    tickets.zero();
+    meta.reset(ctx, (size_t)max_jobs);
+    counts.reset(ctx, (size_t)B * max_tiles * 2 + max_jobs);  // tiles per job halve as jobs double
+  }
+  unsigned short* keys16 = reinterpret_cast<unsigned short*>(keys_a.p);
   for (; (span >> level) > kLocal; ++level) {
     const int segs = 1 << level, S = span >> level, jobs = B * segs;
     DBuf<int> job_n(ctx, jobs);
@@ -392,10 +614,22 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
     const int seg_max = std::min(S, max_n);
     kd_bbox_kernel<<<dim3(std::max(1, std::min(ceil_div(seg_max, 2048), 64)), jobs), 256, 0, st>>>(clouds.p, cur, span,
                                                                                                  segs, S, bbox.p);
+    ctx_count_launches(ctx, 2);
+    if (!sort_levels) {
+      const int ntiles = ceil_div(seg_max, kSplitTile);
+      PGS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)jobs * kSplitBins * sizeof(unsigned), st));
+      const dim3 grid(ntiles, jobs);
+      kd_hist_kernel<<<grid, 256, 0, st>>>(clouds.p, cur, span, segs, S, bbox.p, keys16, hist.p, tickets.p, meta.p);
+      kd_part_count_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, keys16, meta.p, counts.p, ntiles);
+      kd_part_scatter_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, cur, other, keys16, meta.p, counts.p, ntiles);
+      ctx_count_launches(ctx, 3);
+      std::swap(cur, other);
+      continue;
+    }
     const int key_bits = level < kFineLevels ? 16 : 8;
     kd_key_kernel<<<dim3(ceil_div(seg_max, 256), jobs), 256, 0, st>>>(clouds.p, cur, span, segs, S, bbox.p, keys_a.p,
                                                                       (float)((1 << key_bits) - 1));
-    ctx_count_launches(ctx, 3);
+    ctx_count_launches(ctx, 1);
     // jobs are laid out back to back with stride S: cloud b, segment s starts at (b*segs + s) * S
     const bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, cur, other, job_n.p, jobs, S, seg_max, key_bits);
     if (in_b) std::swap(cur, other);  // a one-pass sort leaves the order in the other buffer
