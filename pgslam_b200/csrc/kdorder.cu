@@ -13,9 +13,10 @@
 //
 // Build, batched over clouds (blockIdx.y / job index = cloud x segment):
 //   global levels  while a segment spans more than kLocal points: per segment
-//                  bounding box -> widest axis -> key = that coordinate, 16 bits ->
-//                  segmented 2-pass radix sort (sort.cu, one job per segment).
-//                  Positional halving of a sorted segment IS the median split.
+//                  bounding box -> widest axis -> 11-bit key along it -> histogram
+//                  select of the median bin -> stable partition (kd_hist /
+//                  kd_part_count / kd_part_scatter below).  Only the split matters:
+//                  both halves are re-split along their own axis one level down.
 //   local levels   one block per kLocal-point segment finishes the remaining
 //                  levels in shared memory with a bitonic network restricted
 //                  to the (shrinking) sub-segments.
@@ -586,9 +587,9 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
   uint32_t* other = vals_b.p;
   kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, cur, span);
   ctx_count_launches(ctx, 1);
-  // PGS_KD_SPLIT_LEVELS=1 selects the median-split global levels (not yet validated on the GPU:
-  // the default stays the segmented radix sorts every measurement in DESIGN.md was taken with)
-  static const bool sort_levels = !(std::getenv("PGS_KD_SPLIT_LEVELS") && std::atoi(std::getenv("PGS_KD_SPLIT_LEVELS")) != 0);
+  // PGS_KD_SORT_LEVELS=1 brings back the earlier global levels (full segmented radix sorts on
+  // 16 / 8-bit keys) for comparison: 2.2 ms per 96 clouds against 1.1 ms for the median split
+  static const bool sort_levels = std::getenv("PGS_KD_SORT_LEVELS") && std::atoi(std::getenv("PGS_KD_SORT_LEVELS")) != 0;
   int level = 0;
   int n_levels = 0;
   while ((span >> n_levels) > kLocal) ++n_levels;
