@@ -195,6 +195,30 @@ pgs_status pgs_icp_run_batch(pgs_icp *icp, int n_pairs,
                              const pgs_cloud *const *readings,
                              const pgs_cloud *const *references,
                              const double *T_inits, pgs_icp_result *results);
+/* The same for HOST-resident clouds on one or several GPUs of this process:
+ * the candidate loop of LoopCloser::AddNewVertex (LoopCloser.hpp:266-297, and
+ * the worker thread of LoopCloserMT.hpp:45-67) submits all its candidates at
+ * once.  icps[d] are ICP handles with the SAME chain, one per context to use
+ * (normally one context per GPU; two contexts of one GPU are allowed).  Pairs
+ * are cut into contiguous blocks, pair i -> icps[i / ceil(n_pairs/n_devices)]
+ * (the partition of pgslam_b200/dist.py), every device streams its block
+ * through chunked uploads that overlap the registrations, and results[i] is
+ * bit-identical to what pgs_icp_run gives for pair i on any of the devices.
+ * pinned != 0 promises that every buffer is page-locked (cudaHostAlloc /
+ * cudaHostRegister): uploads are then asynchronous.  No NCCL: one process.   */
+typedef struct {
+  const float *features4xN;        /* PM features, column-major 4 x N          */
+  int64_t n;
+  int n_descriptors;               /* optional descriptor blocks, span x N     */
+  const char *const *labels;
+  const int *spans;
+  const float *const *data;
+} pgs_host_cloud;
+pgs_status pgs_icp_run_batch_multi(pgs_icp *const *icps, int n_devices, int n_pairs,
+                                   const pgs_host_cloud *readings,
+                                   const pgs_host_cloud *references,
+                                   const double *T_inits, int pinned,
+                                   pgs_icp_result *results);
 /* Localizer::ComputeOverlapWith (Localizer.hpp:282-348) as one fused call.   */
 pgs_status pgs_icp_probe_overlap(pgs_icp *icp, const pgs_cloud *reading,
                                  const pgs_cloud *reference,
@@ -235,6 +259,9 @@ pgs_status pgs_ctx_set_profiling(pgs_ctx *ctx, int enabled);
  * context's own stream).  Results are bit-identical whatever the split.       */
 pgs_status pgs_ctx_set_batch_streams(pgs_ctx *ctx, int n_streams);
 pgs_status pgs_ctx_last_stage_times(const pgs_ctx *ctx, pgs_stage_times *out);
+/* Scheduling knobs of the hot kernels (never change a result): "match_mode"
+ * 0..3, "pm_blocks", "pm_refill", "pm_pair_w", "pm_leaf_w" (DESIGN.md §6).     */
+pgs_status pgs_ctx_set_option(pgs_ctx *ctx, const char *key, double value);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 // Each function names, in the header, the pgslam call site it serves.
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 #include "filters.cuh"
 #include "icp.cuh"
@@ -52,7 +53,58 @@ pgs_status fail(Ctx* ctx, int code, const std::string& msg) {
   return (pgs_status)code;
 }
 
-#define PGS_API_BEGIN try {
+// Every entry point runs with its context's device current (and puts the caller's device back):
+// a handle may be used from any host thread, whatever device that thread last selected.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const Ctx* c) {
+    if (!c) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != c->device) {
+      PGS_CUDA(cudaSetDevice(c->device));
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// A cloud that belongs to another context of the same device is joined to the consumer's
+// stream for the duration of a call: the consumer waits for everything queued on the owner's
+// stream so far (the upload, filters ...), and when the call has been enqueued the owner's
+// stream waits for the consumer, so a later free / overwrite on the owner's stream cannot
+// overtake the consumer's reads.  A cloud on another DEVICE is rejected.
+struct Borrow {
+  Ctx* consumer;
+  std::vector<Ctx*> owners;
+  explicit Borrow(Ctx* c) : consumer(c) {}
+  void use(const Cloud* cl) {
+    if (!cl) return;
+    cl->wait_ready();
+    Ctx* o = cl->ctx;
+    if (o == consumer) return;
+    if (o->device != consumer->device)
+      throw Error(PGS_INVALID_ARGUMENT, "cloud lives on device " + std::to_string(o->device) + ", the handle on device " +
+                                            std::to_string(consumer->device));
+    for (Ctx* seen : owners)
+      if (seen == o) return;
+    if (!o->cross_ev) PGS_CUDA(cudaEventCreateWithFlags(&o->cross_ev, cudaEventDisableTiming));
+    PGS_CUDA(cudaEventRecord(o->cross_ev, o->stream));
+    PGS_CUDA(cudaStreamWaitEvent(consumer->stream, o->cross_ev, 0));
+    owners.push_back(o);
+  }
+  void use(const pgs_cloud* c) { use(c ? c->c.get() : nullptr); }
+  ~Borrow() {
+    if (owners.empty()) return;
+    if (!consumer->cross_ev && cudaEventCreateWithFlags(&consumer->cross_ev, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(consumer->cross_ev, consumer->stream);
+    for (Ctx* o : owners) cudaStreamWaitEvent(o->stream, consumer->cross_ev, 0);
+  }
+};
+
+#define PGS_API_BEGIN(ctxptr) try { DeviceGuard _dg(ctxptr);
 #define PGS_API_END(ctxptr)                                              \
   }                                                                      \
   catch (const pgs::Error& _ex) { return fail((ctxptr), _ex.code, _ex.what()); } \
@@ -138,9 +190,14 @@ const char* pgs_version(void) { return "pgslam_b200 0.1 (sm_100a)"; }
 
 pgs_status pgs_ctx_create(int device, void* stream, pgs_ctx** out) {
   Ctx* cp = nullptr;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(cp)
   if (!out) throw Error(PGS_INVALID_ARGUMENT, "out is NULL");
   int count = 0;
+  struct Restore {
+    int prev = -1;
+    Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
     throw Error(PGS_CUDA_ERROR, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
@@ -171,15 +228,18 @@ pgs_status pgs_ctx_create(int device, void* stream, pgs_ctx** out) {
 
 void pgs_ctx_destroy(pgs_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->c.device);
-  ctx->c.destroy_resources();
-  delete ctx;
+  try {
+    DeviceGuard dg(&ctx->c);
+    ctx->c.destroy_resources();
+    delete ctx;
+  } catch (...) {
+  }
 }
 
 const char* pgs_last_error(const pgs_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_no_ctx_error.c_str(); }
 
 pgs_status pgs_ctx_synchronize(pgs_ctx* ctx) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   ctx->c.sync();
   PGS_API_END(&ctx->c)
 }
@@ -239,6 +299,22 @@ pgs_status pgs_ctx_set_batch_streams(pgs_ctx* ctx, int n_streams) {
   return PGS_OK;
 }
 
+pgs_status pgs_ctx_set_option(pgs_ctx* ctx, const char* key, double value) {
+  PGS_API_BEGIN(&ctx->c)
+  if (!key) throw Error(PGS_INVALID_ARGUMENT, "pgs_ctx_set_option: key is NULL");
+  const std::string k(key);
+  Tuning& t = ctx->c.tune;
+  const int v = (int)value;
+  if (k == "match_mode") { if (v < 0 || v > 3) throw Error(PGS_INVALID_ARGUMENT, "match_mode must be 0..3"); t.match_mode = v; }
+  else if (k == "pm_blocks") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_blocks must be 1..32"); t.pm_blocks = v; }
+  else if (k == "pm_refill") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_refill must be 1..32"); t.pm_refill = v; }
+  else if (k == "pm_pair_w") { if (v < 1) throw Error(PGS_INVALID_ARGUMENT, "pm_pair_w must be >= 1"); t.pm_pair_w = v; }
+  else if (k == "pm_leaf_w") { if (v < 1) throw Error(PGS_INVALID_ARGUMENT, "pm_leaf_w must be >= 1"); t.pm_leaf_w = v; }
+  else if (k == "batch_chunk") { if (v < 1 || v > 4096) throw Error(PGS_INVALID_ARGUMENT, "batch_chunk must be 1..4096"); t.batch_chunk = v; }
+  else throw Error(PGS_INVALID_ARGUMENT, "pgs_ctx_set_option: unknown key " + k);
+  PGS_API_END(&ctx->c)
+}
+
 pgs_status pgs_ctx_last_stage_times(const pgs_ctx* ctx, pgs_stage_times* out) {
   *out = ctx->c.times;
   return PGS_OK;
@@ -246,10 +322,9 @@ pgs_status pgs_ctx_last_stage_times(const pgs_ctx* ctx, pgs_stage_times* out) {
 
 // ---- DataPoints ---------------------------------------------------------------
 pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, int on_device, pgs_cloud** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   if (!out || n < 0 || (n > 0 && !features4xN)) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_create: bad arguments");
   if (n > 0x7fffffff - 1024) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_create: too many points");
-  PGS_CUDA(cudaSetDevice(ctx->c.device));
   auto h = std::make_unique<pgs_cloud>();
   h->c = std::make_unique<Cloud>(&ctx->c);
   h->c->n = n;
@@ -266,7 +341,7 @@ pgs_status pgs_cloud_create(pgs_ctx* ctx, const float* features4xN, int64_t n, i
 
 pgs_status pgs_cloud_set_descriptor(pgs_cloud* c, const char* label, int span, const float* data, int on_device) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   c->c->wait_ready();
   if (span <= 0 || !label) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_set_descriptor: bad arguments");
   Desc& d = c->c->add(label, span);
@@ -276,7 +351,7 @@ pgs_status pgs_cloud_set_descriptor(pgs_cloud* c, const char* label, int span, c
 
 pgs_status pgs_cloud_remove_descriptor(pgs_cloud* c, const char* label) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   if (!c->c->find(label)) throw Error(PGS_INVALID_FIELD, std::string("Cannot find descriptor ") + label);
   c->c->remove(label);
   PGS_API_END(ctx)
@@ -287,7 +362,7 @@ int pgs_cloud_num_descriptors(const pgs_cloud* c) { return (int)c->c->descs.size
 
 pgs_status pgs_cloud_descriptor_info(const pgs_cloud* c, int index, char* label, int cap, int* span) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   if (index < 0 || index >= (int)c->c->descs.size()) throw Error(PGS_INVALID_FIELD, "descriptor index out of range");
   const Desc& d = c->c->descs[index];
   if (label && cap > 0) {
@@ -300,7 +375,7 @@ pgs_status pgs_cloud_descriptor_info(const pgs_cloud* c, int index, char* label,
 
 pgs_status pgs_cloud_get_features(const pgs_cloud* c, float* out4xN, int on_device) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   c->c->wait_ready();
   copy_out(ctx, out4xN, c->c->feat.p, (size_t)c->c->n * sizeof(float4), on_device);
   PGS_API_END(ctx)
@@ -308,7 +383,7 @@ pgs_status pgs_cloud_get_features(const pgs_cloud* c, float* out4xN, int on_devi
 
 pgs_status pgs_cloud_get_descriptor(const pgs_cloud* c, const char* label, float* out, int on_device) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   c->c->wait_ready();
   const Desc* d = c->c->find(label);
   if (!d) throw Error(PGS_INVALID_FIELD, std::string("Cannot find descriptor ") + label);
@@ -318,7 +393,7 @@ pgs_status pgs_cloud_get_descriptor(const pgs_cloud* c, const char* label, float
 
 pgs_status pgs_cloud_copy(const pgs_cloud* c, pgs_cloud** out) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   c->c->wait_ready();
   auto h = std::make_unique<pgs_cloud>();
   h->c = c->c->clone();
@@ -328,31 +403,40 @@ pgs_status pgs_cloud_copy(const pgs_cloud* c, pgs_cloud** out) {
 
 pgs_status pgs_cloud_concatenate(pgs_cloud* a, const pgs_cloud* b) {
   Ctx* ctx = a->c->ctx;
-  PGS_API_BEGIN
-  a->c->wait_ready(); b->c->wait_ready();
+  PGS_API_BEGIN(ctx)
+  Borrow bw(ctx);
+  bw.use(a); bw.use(b);
   concatenate_cloud(*a->c, *b->c);
   PGS_API_END(ctx)
 }
 
-void pgs_cloud_destroy(pgs_cloud* c) { delete c; }
+void pgs_cloud_destroy(pgs_cloud* c) {
+  if (!c) return;
+  try {
+    DeviceGuard dg(c->c ? c->c->ctx : nullptr);
+    delete c;
+  } catch (...) {
+  }
+}
 
 // ---- Transformation -------------------------------------------------------------
 pgs_status pgs_rigid_transform(pgs_cloud* c, const double T[16]) {
   Ctx* ctx = c->c->ctx;
-  PGS_API_BEGIN
+  PGS_API_BEGIN(ctx)
   c->c->wait_ready();
   rigid_transform_cloud(*c->c, T);
   PGS_API_END(ctx)
 }
 
 pgs_status pgs_cloud_assemble(pgs_ctx* ctx, int n, const pgs_cloud* const* clouds, const double* T, pgs_cloud** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   if (n < 1) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_assemble: need at least one cloud");
-  for (int i = 0; i < n; ++i) clouds[i]->c->wait_ready();
+  Borrow bw(&ctx->c);
+  for (int i = 0; i < n; ++i) bw.use(clouds[i]);
   auto h = std::make_unique<pgs_cloud>();
-  h->c = clouds[0]->c->clone();
+  h->c = clouds[0]->c->clone(&ctx->c);
   for (int i = 1; i < n; ++i) {
-    auto tmp = clouds[i]->c->clone();
+    auto tmp = clouds[i]->c->clone(&ctx->c);
     rigid_transform_cloud(*tmp, T + 16 * i);
     concatenate_cloud(*h->c, *tmp);
   }
@@ -362,7 +446,7 @@ pgs_status pgs_cloud_assemble(pgs_ctx* ctx, int n, const pgs_cloud* const* cloud
 
 // ---- DataPointsFilters ------------------------------------------------------------
 pgs_status pgs_filters_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t len, pgs_filters** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   YamlNode root = parse_yaml(std::string(yaml, len));
   auto h = std::make_unique<pgs_filters>();
   h->ctx = &ctx->c;
@@ -372,7 +456,7 @@ pgs_status pgs_filters_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t l
 }
 
 pgs_status pgs_filters_create(pgs_ctx* ctx, pgs_filters** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_filters>();
   h->ctx = &ctx->c;
   *out = h.release();
@@ -380,7 +464,7 @@ pgs_status pgs_filters_create(pgs_ctx* ctx, pgs_filters** out) {
 }
 
 pgs_status pgs_filters_append(pgs_filters* f, const char* name, const char* const* kv, int nkv) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(f->ctx)
   f->mods.push_back(create_module(Kind::DataPointsFilter, name, kv_params(kv, nkv)));
   PGS_API_END(f->ctx)
 }
@@ -388,10 +472,12 @@ pgs_status pgs_filters_append(pgs_filters* f, const char* name, const char* cons
 int pgs_filters_count(const pgs_filters* f) { return (int)f->mods.size(); }
 
 pgs_status pgs_filters_apply(pgs_filters* f, pgs_cloud* c) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(f->ctx)
+  // the filters run on the CLOUD's context: its buffers are reallocated on that stream
   c->c->wait_ready();
+  if (c->c->ctx->device != f->ctx->device) throw Error(PGS_INVALID_ARGUMENT, "cloud and filters live on different devices");
   std::vector<Cloud*> cl{c->c.get()};
-  apply_filters(f->ctx, f->mods, cl);
+  apply_filters(c->c->ctx, f->mods, cl);
   PGS_API_END(f->ctx)
 }
 
@@ -399,7 +485,7 @@ void pgs_filters_destroy(pgs_filters* f) { delete f; }
 
 // ---- Matcher -----------------------------------------------------------------------
 pgs_status pgs_matcher_create(pgs_ctx* ctx, const char* name, const char* const* kv, int nkv, pgs_matcher** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_matcher>();
   h->ctx = &ctx->c;
   h->mod = create_module(Kind::Matcher, name, kv_params(kv, nkv));
@@ -409,8 +495,9 @@ pgs_status pgs_matcher_create(pgs_ctx* ctx, const char* name, const char* const*
 }
 
 pgs_status pgs_matcher_init(pgs_matcher* m, const pgs_cloud* reference) {
-  PGS_API_BEGIN
-  reference->c->wait_ready();
+  PGS_API_BEGIN(m->ctx)
+  Borrow bw(m->ctx);
+  bw.use(reference);
   std::vector<std::unique_ptr<Index>> idx;
   build_indices(m->ctx, {reference->c->feat.p}, {(int)reference->c->n}, nullptr, idx);
   m->index = std::move(idx[0]);
@@ -420,8 +507,9 @@ pgs_status pgs_matcher_init(pgs_matcher* m, const pgs_cloud* reference) {
 int pgs_matcher_knn(const pgs_matcher* m) { return (int)m->mod.integer("knn"); }
 
 pgs_status pgs_matcher_find(pgs_matcher* m, const pgs_cloud* reading, int32_t* ids, float* dists2, int on_device) {
-  PGS_API_BEGIN
-  reading->c->wait_ready();
+  PGS_API_BEGIN(m->ctx)
+  Borrow bw(m->ctx);
+  bw.use(reading);
   const int k = (int)m->mod.integer("knn");
   const size_t cnt = (size_t)reading->c->n * k;
   if (on_device) {
@@ -441,7 +529,7 @@ void pgs_matcher_destroy(pgs_matcher* m) { delete m; }
 
 // ---- OutlierFilters ------------------------------------------------------------------
 pgs_status pgs_outliers_create(pgs_ctx* ctx, pgs_outliers** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_outliers>();
   h->ctx = &ctx->c;
   *out = h.release();
@@ -449,16 +537,16 @@ pgs_status pgs_outliers_create(pgs_ctx* ctx, pgs_outliers** out) {
 }
 
 pgs_status pgs_outliers_append(pgs_outliers* o, const char* name, const char* const* kv, int nkv) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(o->ctx)
   o->mods.push_back(create_module(Kind::OutlierFilter, name, kv_params(kv, nkv)));
   PGS_API_END(o->ctx)
 }
 
 pgs_status pgs_outliers_compute(pgs_outliers* o, const pgs_cloud* reading, const pgs_cloud* reference,
                                 const int32_t* ids, const float* dists2, int k, float* weights, int on_device) {
-  PGS_API_BEGIN
-  reading->c->wait_ready();
-  reference->c->wait_ready();
+  PGS_API_BEGIN(o->ctx)
+  Borrow bw(o->ctx);
+  bw.use(reading); bw.use(reference);
   const int64_t nk = reading->c->n * k;
   if (on_device) {
     outlier_weights_device(o->ctx, o->mods, dists2, nk, weights, reading->c.get(), reference->c.get(), ids, k);
@@ -477,7 +565,7 @@ void pgs_outliers_destroy(pgs_outliers* o) { delete o; }
 
 // ---- ErrorMinimizer --------------------------------------------------------------------
 pgs_status pgs_minimizer_create(pgs_ctx* ctx, const char* name, const char* const* kv, int nkv, pgs_minimizer** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_minimizer>();
   h->ctx = &ctx->c;
   h->mod = create_module(Kind::ErrorMinimizer, name, kv_params(kv, nkv));
@@ -488,8 +576,9 @@ pgs_status pgs_minimizer_create(pgs_ctx* ctx, const char* name, const char* cons
 pgs_status pgs_minimizer_compute(pgs_minimizer* e, const pgs_cloud* reading, const pgs_cloud* reference,
                                  const int32_t* ids, const float* dists2, const float* weights, int k, int on_device,
                                  pgs_min_result* out) {
-  PGS_API_BEGIN
-  reading->c->wait_ready(); reference->c->wait_ready();
+  PGS_API_BEGIN(e->ctx)
+  Borrow bw(e->ctx);
+  bw.use(reading); bw.use(reference);
   const size_t nk = (size_t)reading->c->n * k;
   if (on_device) {
     minimize_device(e->ctx, e->mod, *reading->c, *reference->c, ids, dists2, weights, k, out);
@@ -508,7 +597,7 @@ void pgs_minimizer_destroy(pgs_minimizer* e) { delete e; }
 
 // ---- ICP / ICPSequence ---------------------------------------------------------------------
 pgs_status pgs_icp_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t len, pgs_icp** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_icp>();
   h->ctx = &ctx->c;
   h->cfg = chain_from_yaml(std::string(yaml, len));
@@ -518,7 +607,7 @@ pgs_status pgs_icp_create_from_yaml(pgs_ctx* ctx, const char* yaml, size_t len, 
 }
 
 pgs_status pgs_icp_create_default(pgs_ctx* ctx, pgs_icp** out) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(&ctx->c)
   auto h = std::make_unique<pgs_icp>();
   h->ctx = &ctx->c;
   h->cfg = chain_default();
@@ -538,8 +627,9 @@ pgs_minimizer* pgs_icp_minimizer(pgs_icp* icp) { return &icp->minimizer; }
 
 pgs_status pgs_icp_run(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference, const double T_init[16],
                        pgs_icp_result* out) {
-  PGS_API_BEGIN
-  reading->c->wait_ready(); reference->c->wait_ready();
+  PGS_API_BEGIN(icp->ctx)
+  Borrow bw(icp->ctx);
+  bw.use(reading); bw.use(reference);
   std::vector<const Cloud*> rd{reading->c.get()}, rf{reference->c.get()};
   engine_of(icp).run_batch(rd, rf, T_init, out);
   if (out->status != PGS_OK) {
@@ -552,8 +642,9 @@ pgs_status pgs_icp_run(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* 
 }
 
 pgs_status pgs_icp_set_map(pgs_icp* icp, const pgs_cloud* map) {
-  PGS_API_BEGIN
-  map->c->wait_ready();
+  PGS_API_BEGIN(icp->ctx)
+  Borrow bw(icp->ctx);
+  bw.use(map);
   engine_of(icp).set_map(*map->c);
   PGS_API_END(icp->ctx)
 }
@@ -561,8 +652,9 @@ pgs_status pgs_icp_set_map(pgs_icp* icp, const pgs_cloud* map) {
 int pgs_icp_has_map(const pgs_icp* icp) { return icp->engine && icp->engine->has_map(); }
 
 pgs_status pgs_icp_run_sequence(pgs_icp* icp, const pgs_cloud* reading, const double T_init[16], pgs_icp_result* out) {
-  PGS_API_BEGIN
-  reading->c->wait_ready();
+  PGS_API_BEGIN(icp->ctx)
+  Borrow bw(icp->ctx);
+  bw.use(reading);
   engine_of(icp).run_sequence(*reading->c, T_init, out);
   if (out->status != PGS_OK) return fail(icp->ctx, out->status, "ICPSequence failed for this reading");
   PGS_API_END(icp->ctx)
@@ -570,12 +662,13 @@ pgs_status pgs_icp_run_sequence(pgs_icp* icp, const pgs_cloud* reading, const do
 
 pgs_status pgs_icp_run_batch(pgs_icp* icp, int n_pairs, const pgs_cloud* const* readings,
                              const pgs_cloud* const* references, const double* T_inits, pgs_icp_result* results) {
-  PGS_API_BEGIN
+  PGS_API_BEGIN(icp->ctx)
   if (n_pairs <= 0) return PGS_OK;
   std::vector<const Cloud*> rd(n_pairs), rf(n_pairs);
+  Borrow bw(icp->ctx);
   for (int i = 0; i < n_pairs; ++i) {
-    readings[i]->c->wait_ready();
-    references[i]->c->wait_ready();
+    bw.use(readings[i]);
+    bw.use(references[i]);
     rd[i] = readings[i]->c.get();
     rf[i] = references[i]->c.get();
   }
@@ -590,13 +683,108 @@ pgs_status pgs_icp_run_batch(pgs_icp* icp, int n_pairs, const pgs_cloud* const* 
   PGS_API_END(icp->ctx)
 }
 
+namespace {
+// host-resident pairs: every chunk is uploaded into the worker context that registers it
+struct HostSource : PairSource {
+  const pgs_host_cloud* rd;
+  const pgs_host_cloud* rf;
+  int base;  // first pair of this device's block
+  int mode;  // on_device mode of the uploads: 2 pinned (asynchronous), 0 pageable
+  std::unique_ptr<Cloud> upload(Ctx* ctx, const pgs_host_cloud& h) {
+    if (h.n < 0 || (h.n > 0 && !h.features4xN)) throw Error(PGS_INVALID_ARGUMENT, "pgs_host_cloud: bad features");
+    if (h.n > 0x7fffffff - 1024) throw Error(PGS_INVALID_ARGUMENT, "pgs_host_cloud: too many points");
+    auto c = std::make_unique<Cloud>(ctx);
+    c->n = h.n;
+    const size_t bytes = (size_t)h.n * sizeof(float4);
+    if (mode == 2) {
+      c->feat.adopt(ctx, static_cast<float4*>(upload_async(ctx, h.features4xN, bytes, &c->ready)), (size_t)h.n);
+    } else {
+      c->feat.reset(ctx, (size_t)h.n);
+      if (bytes) PGS_CUDA(cudaMemcpyAsync(c->feat.p, h.features4xN, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int d = 0; d < h.n_descriptors; ++d) {
+      if (!h.labels || !h.spans || !h.data || !h.labels[d] || h.spans[d] <= 0 || !h.data[d])
+        throw Error(PGS_INVALID_ARGUMENT, "pgs_host_cloud: bad descriptor block");
+      Desc& desc = c->add(h.labels[d], h.spans[d]);
+      const size_t db = (size_t)h.n * h.spans[d] * sizeof(float);
+      if (mode == 2) copy_in(ctx, desc.data.p, h.data[d], db, 2);
+      else if (db) PGS_CUDA(cudaMemcpyAsync(desc.data.p, h.data[d], db, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return c;
+  }
+  void fetch(Ctx* ctx, int lo, int hi, FetchedPairs& out) override {
+    for (int i = lo; i < hi; ++i) {
+      out.owned.push_back(upload(ctx, rd[base + i]));
+      out.readings.push_back(out.owned.back().get());
+      out.owned.push_back(upload(ctx, rf[base + i]));
+      out.references.push_back(out.owned.back().get());
+    }
+  }
+  void before_run(Ctx*, FetchedPairs& f) override {
+    for (auto& c : f.owned) c->wait_ready();  // the compute stream joins the uploads here, not earlier
+  }
+};
+}  // namespace
+
+pgs_status pgs_icp_run_batch_multi(pgs_icp* const* icps, int n_devices, int n_pairs, const pgs_host_cloud* readings,
+                                   const pgs_host_cloud* references, const double* T_inits, int pinned,
+                                   pgs_icp_result* results) {
+  Ctx* ctx0 = (icps && n_devices > 0 && icps[0]) ? icps[0]->ctx : nullptr;
+  PGS_API_BEGIN(ctx0)
+  if (!icps || n_devices < 1 || n_pairs < 0 || (n_pairs > 0 && (!readings || !references || !results)))
+    throw Error(PGS_INVALID_ARGUMENT, "pgs_icp_run_batch_multi: bad arguments");
+  for (int d = 0; d < n_devices; ++d) {
+    if (!icps[d]) throw Error(PGS_INVALID_ARGUMENT, "pgs_icp_run_batch_multi: NULL ICP handle");
+    for (int e = 0; e < d; ++e)
+      if (icps[e]->ctx == icps[d]->ctx) throw Error(PGS_INVALID_ARGUMENT, "pgs_icp_run_batch_multi: two handles share a context");
+  }
+  if (n_pairs == 0) return PGS_OK;
+  const int per = (n_pairs + n_devices - 1) / n_devices;
+  std::vector<std::thread> threads;
+  std::vector<std::unique_ptr<Error>> errors(n_devices);
+  for (int d = 0; d < n_devices; ++d) {
+    const int lo = std::min(d * per, n_pairs), hi = std::min((d + 1) * per, n_pairs);
+    if (lo >= hi) continue;
+    threads.emplace_back([=, &errors]() {
+      try {
+        DeviceGuard dg(icps[d]->ctx);
+        HostSource src;
+        src.rd = readings;
+        src.rf = references;
+        src.base = lo;
+        src.mode = pinned ? 2 : 0;
+        engine_of(icps[d]).run_batch_source(hi - lo, src, T_inits ? T_inits + (size_t)16 * lo : nullptr, results + lo);
+      } catch (const Error& e) {
+        errors[d] = std::make_unique<Error>(e);
+      } catch (const std::exception& e) {
+        errors[d] = std::make_unique<Error>(PGS_CUDA_ERROR, e.what());
+      }
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int d = 0; d < n_devices; ++d)
+    if (errors[d]) {
+      icps[d]->ctx->last_error = errors[d]->what();
+      throw *errors[d];
+    }
+  bool any_ok = false;
+  int first_bad = PGS_OK;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (results[i].status == PGS_OK) any_ok = true;
+    else if (first_bad == PGS_OK) first_bad = results[i].status;
+  }
+  if (!any_ok) return fail(ctx0, first_bad, "every pair of the batch failed");
+  PGS_API_END(ctx0)
+}
+
 pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
                                  const double T_world_robot[16], double* weighted_point_used_ratio) {
-  PGS_API_BEGIN
-  reading->c->wait_ready(); reference->c->wait_ready();
+  PGS_API_BEGIN(icp->ctx)
   Ctx* ctx = icp->ctx;
+  Borrow bw(ctx);
+  bw.use(reading); bw.use(reference);
   // Localizer.hpp:309-347, module by module, without leaving the device
-  auto ref = reference->c->clone();
+  auto ref = reference->c->clone(ctx);
   std::vector<Cloud*> rl{ref.get()};
   apply_filters(ctx, icp->cfg.reference_filters, rl);
   pgs_matcher m;
@@ -605,7 +793,7 @@ pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const p
   std::vector<std::unique_ptr<Index>> idx;
   build_indices(ctx, {ref->feat.p}, {(int)ref->n}, nullptr, idx);
   m.index = std::move(idx[0]);
-  auto rd = reading->c->clone();
+  auto rd = reading->c->clone(ctx);
   std::vector<Cloud*> dl{rd.get()};
   apply_filters(ctx, icp->cfg.reading_filters, dl);
   rigid_transform_cloud(*rd, T_world_robot);
@@ -625,11 +813,12 @@ pgs_status pgs_icp_probe_overlap(pgs_icp* icp, const pgs_cloud* reading, const p
 
 pgs_status pgs_icp_probe_residual(pgs_icp* icp, const pgs_cloud* reading, const pgs_cloud* reference,
                                   const double T[16], double* residual) {
-  PGS_API_BEGIN
-  reading->c->wait_ready(); reference->c->wait_ready();
+  PGS_API_BEGIN(icp->ctx)
   Ctx* ctx = icp->ctx;
+  Borrow bw(ctx);
+  bw.use(reading); bw.use(reference);
   // LoopCloser.hpp:346-362: raw candidate cloud, un-centred, unfiltered
-  auto rd = reading->c->clone();
+  auto rd = reading->c->clone(ctx);
   rigid_transform_cloud(*rd, T);
   pgs_matcher m;
   m.ctx = ctx;

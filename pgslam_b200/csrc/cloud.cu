@@ -55,6 +55,25 @@ void Ctx::upload_small(void* dst, const void* src, size_t bytes) {
   ++launches;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v && *v ? std::atoi(v) : dflt;
+}
+
+#ifndef PGS_MATCH_MODE_DEFAULT
+#define PGS_MATCH_MODE_DEFAULT 0
+#endif
+#ifndef PGS_PM_MIN_BLOCKS
+#define PGS_PM_MIN_BLOCKS 10
+#endif
+Tuning::Tuning()
+    : match_mode(env_int("PGS_MATCH_MODE", PGS_MATCH_MODE_DEFAULT)),
+      pm_blocks(env_int("PGS_PM_BLOCKS", PGS_PM_MIN_BLOCKS)),
+      pm_refill(env_int("PGS_PM_REFILL", 4)),
+      pm_pair_w(env_int("PGS_PM_PAIR_W", 5)),
+      pm_leaf_w(env_int("PGS_PM_LEAF_W", 3)),
+      batch_chunk(env_int("PGS_BATCH_CHUNK", 24)) {}
+
 Ctx* Ctx::worker(int i) {
   while ((int)workers.size() <= i) {
     Ctx* w = new Ctx();
@@ -66,6 +85,7 @@ Ctx* Ctx::worker(int i) {
     w->own_stream = true;
     workers.push_back(w);
   }
+  workers[i]->tune = tune;
   return workers[i];
 }
 
@@ -84,6 +104,7 @@ void Ctx::destroy_resources() {
     if (e) cudaEventDestroy(e);
   if (fork_ev) cudaEventDestroy(fork_ev);
   if (sync_ev) cudaEventDestroy(sync_ev);
+  if (cross_ev) cudaEventDestroy(cross_ev);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream) cudaStreamDestroy(stream);
   pinned = nullptr;

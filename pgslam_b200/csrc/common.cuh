@@ -45,8 +45,21 @@ struct Error : std::runtime_error {
 // are independent (pgslam-MT drives the localizer and the loop closer from two
 // host threads, LocalizerMT.hpp:47 / LoopCloserMT.hpp:41).
 // ---------------------------------------------------------------------------
+// Tuning knobs of the hot kernels (pgs_ctx_set_option; defaults from PGS_* environment
+// variables).  None of them changes a result - only how the work is scheduled.
+struct Tuning {
+  int match_mode;     // 0 descent from 10 levels up + climb, 1 cell-guided start, 2 persistent lanes from
+                      // the root, 3 persistent lanes + cell-guided start
+  int pm_blocks;      // persistent matcher: resident blocks per SM
+  int pm_refill;      // ... idle lanes that trigger a refill
+  int pm_pair_w, pm_leaf_w;  // ... PAIR runs when pairs * pair_w >= leaves * leaf_w
+  int batch_chunk;    // pairs per chunk a batch worker pulls (pgs_icp_run_batch)
+  Tuning();
+};
+
 struct Ctx {
   int device = 0;
+  Tuning tune;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int num_sms = 148;
@@ -82,6 +95,7 @@ struct Ctx {
   // spinning waiter that loses its core finds out late that the device went idle.  The
   // single-registration path keeps the spinning waits (lowest latency).
   bool blocking_waits = false;
+  cudaEvent_t cross_ev = nullptr;  // joins with other contexts' streams (api.cu Borrow)
   cudaEvent_t sync_ev = nullptr;
   void sync() {
     if (!blocking_waits) { PGS_CUDA(cudaStreamSynchronize(stream)); return; }

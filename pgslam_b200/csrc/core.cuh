@@ -95,6 +95,7 @@ static constexpr int kLeaf = 8;  // 8 float4 = one 128-byte line per leaf
 struct TreeView {
   const float4* pts;   // sorted; w = original index (int bits); padded to n_leaves*kLeaf
   const float* nodes;  // 2*P nodes x {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z}; node 0 unused
+  const float* cells;  // 2*P exclusive cells, same layout (index.cu cell_levels_kernel); may be null
   int n;
   int n_leaves;
   int P;      // leaves rounded up to a power of two
@@ -106,7 +107,8 @@ struct Index {
   int n = 0, n_leaves = 0, P = 1, depth = 0;
   DBuf<float4> pts;
   DBuf<float> nodes;
-  TreeView view() const { return TreeView{pts.p, nodes.p, n, n_leaves, P, depth}; }
+  DBuf<float> cells;
+  TreeView view() const { return TreeView{pts.p, nodes.p, cells.p, n, n_leaves, P, depth}; }
 };
 
 // Build one index per input cloud (features only).  If d_shift != nullptr,

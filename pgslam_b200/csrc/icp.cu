@@ -17,6 +17,7 @@
 // to stop launching once every pair has converged.
 #include "icp.cuh"
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -347,12 +348,12 @@ __global__ void shift_points_kernel(float4* __restrict__ pts, int n, const float
 
 // per-pair state initialisation: pose algebra in fp64 on the device so that the
 // reference mean never has to visit the host
-__global__ void init_state_kernel(PairState* __restrict__ states, const double* __restrict__ T_refIn_refMean,
+__global__ void init_state_kernel(PairState* __restrict__ states, const double* const* __restrict__ T_refIn_refMean,
                                   int n_pairs) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   PairState& st = states[p];
-  for (int i = 0; i < 16; ++i) st.T_refIn_refMean[i] = T_refIn_refMean[16 * p + i];
+  for (int i = 0; i < 16; ++i) st.T_refIn_refMean[i] = T_refIn_refMean[p][i];
   double inv[16];
   m4_rigid_inv(st.T_refIn_refMean, inv);
   m4_mul(inv, st.T_init, st.T_refMean_dataIn);
@@ -475,6 +476,210 @@ match_kernel(const PairView* __restrict__ views, PairState* __restrict__ states,
   }
   v.match_pos[i] = acc.pos;
   v.match_d2[i] = acc.dist();
+}
+
+// ---------------------------------------------------------------------------
+// Cell test (index.cu cell_levels_kernel): true iff every reference point OUTSIDE the cell of
+// `node` is strictly farther from q than `bound`, i.e. the search may start at `node`.
+// m = the smallest of the six face gaps, each computed with the subtraction the distance
+// itself uses; a point beyond a face has |q_a - p_a| >= that gap after rounding (monotone),
+// so its distance is >= fl(m*m).  Strict '>' keeps equal-distance lower-index points reachable.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool cell_contains(const unsigned long long* __restrict__ cells8, unsigned node,
+                                              const QueryPk& q, float bound) {
+  const unsigned long long* __restrict__ cb = cells8 + (size_t)node * 3;
+  float ax, ay, bx, by, cl, ch;
+  unpack_f32x2(sub_f32x2(q.xy, __ldg(cb)), ax, ay);      // q - lo
+  unpack_f32x2(sub_f32x2(__ldg(cb + 1), q.xy), bx, by);  // hi - q
+  unpack_f32x2(sub_f32x2(__ldg(cb + 2), q.zz), cl, ch);  // lo.z - q.z, hi.z - q.z
+  const float m = fminf(fminf(fminf(ax, ay), fminf(bx, by)), fminf(-cl, ch));
+  return m > 0.f && __fmul_rn(m, m) > bound;
+}
+
+// match_kernel with the cell test instead of the fixed 10-level descent + climb: the search
+// starts at the lowest ancestor of the previous match's leaf whose cell holds the candidate
+// ball, and never climbs.
+__global__ void PGS_MATCH_BOUNDS
+match_cells_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_r) return;
+  const Xf T = st.xf;
+  float4 r = v.reading[i];
+  float3 q = xform_rn(T, r.x, r.y, r.z);
+  Best1 acc;
+  acc.init(maxr2);
+  const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
+  unsigned node = 1u;
+  int depth = 0;
+  if (pp >= 0) {
+    const float4 c = __ldg(v.tree.pts + pp);
+    acc.offer(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pp);
+    const unsigned long long* __restrict__ cells8 = reinterpret_cast<const unsigned long long*>(v.tree.cells);
+    const QueryPk qp = pack_query(q.x, q.y, q.z);
+    node = (unsigned)(v.tree.P + pp / kLeaf);
+    depth = v.tree.depth;
+    while (depth > 0 && !cell_contains(cells8, node, qp, acc.bound())) { node >>= 1; --depth; }
+  }
+  knn_traverse_from(v.tree, node, depth, q.x, q.y, q.z, acc, 0, -1);
+  v.match_pos[i] = acc.pos;
+  v.match_d2[i] = acc.dist();
+}
+
+// ---------------------------------------------------------------------------
+// Persistent matcher: warps pull ranges of queries from a ticket counter and every LANE pulls
+// its next query as soon as its search ends (dynamic refill), so a lane whose walk was short
+// does not idle until the longest walk of its warp finishes.  A search is a small state
+// machine - CELL (climb one ancestor, one cell test), PAIR (test the two children of a node),
+// LEAF (scan 8 points) - and each trip of the warp's loop runs the phase most lanes wait in.
+// A pending sibling is revisited through its parent's PAIR step (restricted to that child), so
+// there is no separate "pop" phase to diverge into.  Results are the same exact (distance,
+// index) minima as match_kernel's: the traversal order cannot change an exact minimum.
+// ---------------------------------------------------------------------------
+#ifndef PGS_PM_MIN_BLOCKS
+#define PGS_PM_MIN_BLOCKS 10
+#endif
+constexpr int kPmRange = 2048;  // queries per ticket
+
+enum { PH_IDLE = 0, PH_CELL = 1, PH_PAIR = 2, PH_LEAF = 3 };
+
+template <bool kUseCells>
+__global__ void __launch_bounds__(128, PGS_PM_MIN_BLOCKS)
+match_persistent_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2,
+                        int ranges_per_pair, unsigned n_tickets, unsigned* __restrict__ ticket, int refill_min,
+                        int pair_w, int leaf_w) {
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= n_tickets) return;
+    const int pair = (int)(t / (unsigned)ranges_per_pair);
+    PairState& st = states[pair];
+    if (!st.active) continue;
+    const PairView v = views[pair];
+    int next = (int)(t % (unsigned)ranges_per_pair) * kPmRange;
+    if (next >= v.n_r) continue;
+    const int q1 = min(next + kPmRange, v.n_r);
+    const bool seeded = st.iterations > 0;
+    const int D = v.tree.depth, P = v.tree.P;
+    const ulonglong2* __restrict__ nodes16 = reinterpret_cast<const ulonglong2*>(v.tree.nodes);
+    const unsigned long long* __restrict__ cells8 = reinterpret_cast<const unsigned long long*>(v.tree.cells);
+
+    int qi = -1, pos = -1, depth = 0, phase = PH_IDLE;
+    unsigned node = 1u, trail = 0u, mode = 0u;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    unsigned long long key = 0ull;
+    for (;;) {
+      // ---- refill -------------------------------------------------------------------
+      const unsigned bi = __ballot_sync(FULL, phase == PH_IDLE);
+      if (bi) {
+        const int nidle = __popc(bi);
+        if (next < q1) {
+          if (nidle >= refill_min || bi == FULL) {
+            const int my = next + __popc(bi & lt_mask);
+            if (phase == PH_IDLE && my < q1) {
+              qi = my;
+              const Xf T = st.xf;
+              const float4 r = v.reading[qi];
+              const float3 q = xform_rn(T, r.x, r.y, r.z);
+              qx = q.x; qy = q.y; qz = q.z;
+              key = make_key(maxr2, 0x7fffffff);
+              pos = -1;
+              node = 1u; depth = 0; trail = 0u; mode = 0u;
+              phase = D == 0 ? PH_LEAF : PH_PAIR;
+              const int pp = seeded ? v.match_pos[qi] : -1;
+              if (pp >= 0) {
+                const float4 c = __ldg(v.tree.pts + pp);
+                const unsigned long long nk = make_key(dist2_rn(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+                if (nk < key) { key = nk; pos = pp; }
+                if (kUseCells && D > 0) { node = (unsigned)(P + pp / kLeaf); depth = D; phase = PH_CELL; }
+              }
+            }
+            next += nidle;
+          }
+        } else if (bi == FULL) {
+          break;
+        }
+      }
+      const QueryPk qp = pack_query(qx, qy, qz);
+      // ---- CELL: cheap, runs whenever a lane is looking for its start node ------------------
+      if (kUseCells && phase == PH_CELL) {
+        if (depth == 0 || cell_contains(cells8, node, qp, key_dist(key))) {
+          trail = 0u; mode = 0u;
+          phase = depth == D ? PH_LEAF : PH_PAIR;
+        } else {
+          node >>= 1; --depth;
+        }
+      }
+      // ---- PAIR or LEAF: the phase that serves more lanes per issue slot --------------------
+      const unsigned bp = __ballot_sync(FULL, phase == PH_PAIR);
+      const unsigned bl = __ballot_sync(FULL, phase == PH_LEAF);
+      bool go_pop = false;
+      if (bp && (!bl || __popc(bp) * pair_w >= __popc(bl) * leaf_w)) {
+        if (phase == PH_PAIR) {
+          const ulonglong2* __restrict__ c = nodes16 + (size_t)node * 3;  // both children: 48 bytes
+          const ulonglong2 a = __ldg(c), b = __ldg(c + 1), e = __ldg(c + 2);
+          const float lb0 = box_lb_packed(qp, a.x, a.y, b.x);
+          const float lb1 = box_lb_packed(qp, b.y, e.x, e.y);
+          const float bound = key_dist(key);
+          bool ok;
+          unsigned child, pend;
+          if (mode & 2u) {  // revisit of a pending sibling: only that child is of interest
+            child = mode & 1u;
+            ok = (child ? lb1 : lb0) <= bound;
+            pend = 0u;
+          } else {
+            const bool near1 = lb1 < lb0;
+            const float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
+            child = near1 ? 1u : 0u;
+            ok = lbn <= bound;
+            pend = (lbf <= bound) ? 1u : 0u;
+          }
+          mode = 0u;
+          if (ok) {
+            trail = (trail << 1) | pend;
+            node = node * 2u + child;
+            ++depth;
+            if (depth == D) phase = PH_LEAF;
+          } else {
+            go_pop = true;
+          }
+        }
+      } else if (bl) {
+        if (phase == PH_LEAF) {
+          const int leaf = (int)node - P;
+          if (leaf < v.tree.n_leaves) {
+            const float4* __restrict__ lp = v.tree.pts + (size_t)leaf * kLeaf;
+#pragma unroll
+            for (int j = 0; j < kLeaf; ++j) {
+              const float4 p = __ldg(lp + j);
+              const unsigned long long nk = make_key(dist2_rn_packed(qp.xy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+              if (nk < key) { key = nk; pos = leaf * kLeaf + j; }
+            }
+          }
+          go_pop = true;
+        }
+      }
+      if (go_pop) {
+        if (trail == 0u) {
+          v.match_pos[qi] = pos;
+          v.match_d2[qi] = pos < 0 ? kInfF : key_dist(key);
+          phase = PH_IDLE;
+        } else {
+          const int up = __ffs(trail) - 1;
+          node >>= up; depth -= up; trail >>= up;  // node: the child whose sibling is pending
+          mode = 2u | ((node & 1u) ^ 1u);
+          node >>= 1; --depth; trail >>= 1;        // its parent; the sibling is entered from there
+          phase = PH_PAIR;
+        }
+      }
+    }
+  }
 }
 
 // KDTreeMatcher knn > 1: every reading point keeps its K nearest (ascending, ties -> lower
@@ -795,10 +1000,13 @@ __global__ void fixed_limits_kernel(PairState* __restrict__ states, IcpParams P,
 #endif
 __global__ void __launch_bounds__(256, PGS_ACC_MIN_BLOCKS)
 accumulate_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int* n_active,
-                  volatile int* h_done) {
+                  volatile int* h_done, unsigned* __restrict__ pm_ticket) {
   __shared__ double sh[8][kAcc];
   __shared__ double tot[kAcc];
   __shared__ bool last;
+  // the persistent matcher's ticket counter is cleared here for the next iteration (this kernel
+  // runs between two match launches of the same stream)
+  if (pm_ticket && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *pm_ticket = 0u;
   PairState& st = states[blockIdx.y];
   if (!st.active) return;
   const PairView v = views[blockIdx.y];
@@ -1291,7 +1499,8 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
   std::vector<Cloud*> rp(B);
   for (int b = 0; b < B; ++b) rp[b] = refs[b].get();
   DBuf<float> shift(ctx, (size_t)4 * B);
-  DBuf<double> Tmean(ctx, (size_t)16 * B);
+  auto Tmean_sp = std::make_shared<DBuf<double>>(ctx, (size_t)16 * B);
+  DBuf<double>& Tmean = *Tmean_sp;
   auto compute_mean = [&]() {
     std::vector<const float4*> pts(B);
     std::vector<int> ns(B);
@@ -1346,8 +1555,6 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
       derive_shifted_indices(ctx, src, shift.p, idx);
     }
   }
-  std::vector<double> hT((size_t)16 * B);
-  Tmean.download(hT.data(), hT.size());
   out.clear();
   std::vector<GatherJob> gjobs;
   int gmax = 0;
@@ -1367,6 +1574,8 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
       ctx_count_launches(ctx, 1);
     }
     pr->cloud = std::move(refs[b]);
+    pr->T_mean = Tmean_sp;
+    pr->T_mean_off = (size_t)16 * b;
     out.push_back(std::move(pr));
   }
   DBuf<GatherJob> d_gjobs(ctx, std::max<size_t>(gjobs.size(), 1));
@@ -1375,59 +1584,93 @@ void IcpEngine::prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bo
     gather_vec3_sorted_batched_kernel<<<dim3(ceil_div(gmax, 256), (unsigned)gjobs.size()), 256, 0, s>>>(d_gjobs.p);
     ctx_count_launches(ctx, 1);
   }
-  ctx->sync();  // Tmean on the host (one sync per prepare, not per iteration)
-  for (int b = 0; b < B; ++b) std::memcpy(out[b]->T_refIn_refMean, hT.data() + 16 * b, 16 * sizeof(double));
-  PGS_LAUNCH_CHECK();
+  PGS_LAUNCH_CHECK();  // no host sync: the reference mean never leaves the device
 }
+
+namespace {
+// clouds that already live on the device
+struct ResidentSource : PairSource {
+  const std::vector<const Cloud*>& rd;
+  const std::vector<const Cloud*>& rf;
+  ResidentSource(const std::vector<const Cloud*>& a, const std::vector<const Cloud*>& b) : rd(a), rf(b) {}
+  void fetch(Ctx*, int lo, int hi, FetchedPairs& out) override {
+    out.readings.assign(rd.begin() + lo, rd.begin() + hi);
+    out.references.assign(rf.begin() + lo, rf.begin() + hi);
+  }
+};
+}  // namespace
 
 void IcpEngine::run_batch(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
                           const double* T_inits, pgs_icp_result* results) {
-  const int P = (int)readings.size();
-  // ---- large batches: sub-batches on worker streams ------------------------------
+  ResidentSource src(readings, references);
+  run_batch_source((int)readings.size(), src, T_inits, results);
+}
+
+// A batch is cut into contiguous chunks; `batch_streams` workers (own stream + host thread) pull
+// the next chunk as soon as they finish one, so the latency-bound tail of one chunk's ICP loop
+// overlaps the wide kernels of the others, and a 4096-pair batch (BASELINE C4) never holds more
+// than workers x 2 chunks of temporaries.  Results do not depend on the cut.
+void IcpEngine::run_batch_source(int P, PairSource& src, const double* T_inits, pgs_icp_result* results) {
+  if (P <= 0) return;
   constexpr int kMinPairsPerStream = 4;
-  const int S = ctx_->profiling ? 1 : std::min(ctx_->batch_streams, P / kMinPairsPerStream);
-  if (S > 1) {
-    // everything queued so far on this context's stream (uploads, filters) happens first
-    if (!ctx_->fork_ev) PGS_CUDA(cudaEventCreateWithFlags(&ctx_->fork_ev, cudaEventDisableTiming));
-    PGS_CUDA(cudaEventRecord(ctx_->fork_ev, ctx_->stream));
-    std::vector<std::thread> threads;
-    std::vector<std::unique_ptr<Error>> errors(S);
-    for (int w = 0; w < S; ++w) {
-      Ctx* wc = ctx_->worker(w);
-      PGS_CUDA(cudaStreamWaitEvent(wc->stream, ctx_->fork_ev, 0));
-      threads.emplace_back([this, wc, w, S, P, &readings, &references, T_inits, results, &errors]() {
-        try {
-          PGS_CUDA(cudaSetDevice(wc->device));
-          // interleaved split: iteration counts vary per pair, neighbours share the load
-          std::vector<const Cloud*> rd, rf;
-          std::vector<double> Ti;
-          std::vector<int> which;
-          for (int p = w; p < P; p += S) {
-            which.push_back(p);
-            rd.push_back(readings[p]);
-            rf.push_back(references[p]);
-            if (T_inits) Ti.insert(Ti.end(), T_inits + 16 * p, T_inits + 16 * p + 16);
-          }
-          std::vector<pgs_icp_result> res(which.size());
-          IcpEngine sub(wc, cfg_);
-          sub.run_batch(rd, rf, T_inits ? Ti.data() : nullptr, res.data());
-          for (size_t j = 0; j < which.size(); ++j) results[which[j]] = res[j];
-        } catch (const Error& e) {
-          errors[w] = std::make_unique<Error>(e);
-        } catch (const std::exception& e) {
-          errors[w] = std::make_unique<Error>(PGS_CUDA_ERROR, e.what());
-        }
-      });
-    }
-    for (auto& t : threads) t.join();
-    for (int w = 0; w < S; ++w) {
-      ctx_->launches += ctx_->workers[w]->launches;
-      ctx_->workers[w]->launches = 0;
-    }
-    for (auto& e : errors)
-      if (e) throw *e;
-    return;  // every worker synchronised its stream before returning its results
+  int S = ctx_->profiling ? 1 : std::min(ctx_->batch_streams, P / kMinPairsPerStream);
+  if (S <= 1) {
+    FetchedPairs f;
+    src.fetch(ctx_, 0, P, f);
+    src.before_run(ctx_, f);
+    run_direct(f.readings, f.references, T_inits, results);
+    return;
   }
+  int chunk = std::max(1, ctx_->tune.batch_chunk);
+  if ((long long)S * chunk > P) chunk = std::max(kMinPairsPerStream, ceil_div(P, S));
+  const int n_chunks = ceil_div(P, chunk);
+  S = std::min(S, n_chunks);
+  // everything queued so far on this context's stream (uploads, filters) happens first
+  if (!ctx_->fork_ev) PGS_CUDA(cudaEventCreateWithFlags(&ctx_->fork_ev, cudaEventDisableTiming));
+  PGS_CUDA(cudaEventRecord(ctx_->fork_ev, ctx_->stream));
+  std::vector<std::thread> threads;
+  std::vector<std::unique_ptr<Error>> errors(S);
+  std::atomic<int> next_chunk{0};
+  for (int w = 0; w < S; ++w) {
+    Ctx* wc = ctx_->worker(w);
+    PGS_CUDA(cudaStreamWaitEvent(wc->stream, ctx_->fork_ev, 0));
+    threads.emplace_back([this, wc, w, P, chunk, n_chunks, &next_chunk, &src, T_inits, results, &errors]() {
+      try {
+        PGS_CUDA(cudaSetDevice(wc->device));
+        IcpEngine sub(wc, cfg_);
+        int cur = next_chunk.fetch_add(1);
+        auto fcur = std::make_unique<FetchedPairs>();
+        if (cur < n_chunks) src.fetch(wc, cur * chunk, std::min(P, (cur + 1) * chunk), *fcur);
+        while (cur < n_chunks) {
+          const int nxt = next_chunk.fetch_add(1);
+          auto fnext = std::make_unique<FetchedPairs>();
+          if (nxt < n_chunks) src.fetch(wc, nxt * chunk, std::min(P, (nxt + 1) * chunk), *fnext);
+          const int lo = cur * chunk;
+          src.before_run(wc, *fcur);
+          sub.run_direct(fcur->readings, fcur->references, T_inits ? T_inits + (size_t)16 * lo : nullptr, results + lo);
+          fcur = std::move(fnext);
+          cur = nxt;
+        }
+      } catch (const Error& e) {
+        errors[w] = std::make_unique<Error>(e);
+      } catch (const std::exception& e) {
+        errors[w] = std::make_unique<Error>(PGS_CUDA_ERROR, e.what());
+      }
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int w = 0; w < S; ++w) {
+    ctx_->launches += ctx_->workers[w]->launches;
+    ctx_->workers[w]->launches = 0;
+  }
+  for (auto& e : errors)
+    if (e) throw *e;
+  // every worker synchronised its stream before returning its results
+}
+
+void IcpEngine::run_direct(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
+                           const double* T_inits, pgs_icp_result* results) {
+  const int P = (int)readings.size();
   if (ctx_->profiling) {
     for (auto& e : idx_ev_)
       if (!e) PGS_CUDA(cudaEventCreate(&e));
@@ -1493,14 +1736,14 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
 
   // ---- initial state ---------------------------------------------------------
   std::vector<PairState> hs(P);
-  std::vector<double> hTm((size_t)16 * P);
+  std::vector<const double*> hTm(P);
   int n_active = 0;
   for (int p = 0; p < P; ++p) {
     PairState& st = hs[p];
     std::memset(&st, 0, sizeof(st));
     if (T_inits) std::memcpy(st.T_init, T_inits + 16 * p, 16 * sizeof(double));
     else { st.T_init[0] = st.T_init[5] = st.T_init[10] = st.T_init[15] = 1.0; }
-    std::memcpy(hTm.data() + 16 * p, refs[p]->T_refIn_refMean, 16 * sizeof(double));
+    hTm[p] = refs[p]->T_mean->p + refs[p]->T_mean_off;
     st.status = PGS_OK;
     if (!is_rigid(st.T_init)) st.status = PGS_TRANSFORMATION_ERROR;
     else if (prm.minimizer != MIN_P2POINT && !refs[p]->has_normals) st.status = PGS_INVALID_FIELD;
@@ -1513,9 +1756,9 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     n_active += st.active;
   }
   DBuf<PairState> d_states(ctx, P);
-  DBuf<double> d_Tm(ctx, (size_t)16 * P);
+  DBuf<const double*> d_Tm(ctx, (size_t)P);
   ctx->upload_small(d_states.p, hs.data(), sizeof(PairState) * P);
-  ctx->upload_small(d_Tm.p, hTm.data(), sizeof(double) * 16 * P);
+  ctx->upload_small(d_Tm.p, hTm.data(), sizeof(double*) * P);
   init_state_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, d_Tm.p, P);
   ctx_count_launches(ctx, 1);
 
@@ -1650,6 +1893,16 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     fixed_limits_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, P);
     ctx_count_launches(ctx, 1);
   }
+  const int match_mode = ctx->tune.match_mode, pm_blocks = ctx->tune.pm_blocks, pm_refill = ctx->tune.pm_refill;
+  const int pm_pair_w = ctx->tune.pm_pair_w, pm_leaf_w = ctx->tune.pm_leaf_w;
+  const int pm_ranges = ceil_div(std::max(max_nr, 1), kPmRange);
+  const unsigned pm_tickets = (unsigned)pm_ranges * (unsigned)P;
+  DBuf<unsigned> pm_ticket;
+  if (knn == 1 && match_mode >= 2) {
+    // cleared by accumulate_kernel between two match launches
+    pm_ticket.reset(ctx, 1);
+    pm_ticket.zero();
+  }
   for (int it = 0; it < max_it; ++it) {
     if (*ctx->h_progress) break;
     if (it >= 2) {
@@ -1665,8 +1918,23 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       kev.push_back(e);
     };
     mark();
-    if (knn == 1) match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
-    else launch_match_k(knn, gm, s, d_views.p, d_states.p, prm.max_r2);
+    if (knn == 1) {
+      if (match_mode == 0) {
+        match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+      } else if (match_mode == 1) {
+        match_cells_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+      } else {
+        const dim3 gp((unsigned)std::min<long long>((long long)ctx->num_sms * pm_blocks, (long long)pm_tickets * 4 + 1));
+        if (match_mode == 2)
+          match_persistent_kernel<false><<<gp, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2, pm_ranges, pm_tickets,
+                                                           pm_ticket.p, pm_refill, pm_pair_w, pm_leaf_w);
+        else
+          match_persistent_kernel<true><<<gp, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2, pm_ranges, pm_tickets,
+                                                          pm_ticket.p, pm_refill, pm_pair_w, pm_leaf_w);
+      }
+    } else {
+      launch_match_k(knn, gm, s, d_views.p, d_states.p, prm.max_r2);
+    }
     mark();
     for (int jq = 0; jq < prm.n_quant; ++jq) {
       if (prm.q_var[jq]) {
@@ -1684,7 +1952,7 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
         select_pass_kernel<<<gs, 256, 0, s>>>(d_views.p, d_states.p, prm, jq, pass, d_nactive.p, ctx->d_progress);
     }
     mark();
-    accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress);
+    accumulate_kernel<<<ga, 256, 0, s>>>(d_views.p, d_states.p, prm, d_nactive.p, ctx->d_progress, pm_ticket.p);
     mark();
     for (int jq = 0; jq < prm.n_quant; ++jq) ctx_count_launches(ctx, prm.q_var[jq] ? 0 : 3);
     ctx_count_launches(ctx, 2);
@@ -1884,7 +2152,10 @@ void minimize_device(Ctx* ctx, const Module& minimizer, const Cloud& reading, co
   DBuf<double> Tm(ctx, 16);
   double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   ctx->upload_small(Tm.p, I, sizeof(I));
-  init_state_kernel<<<1, 32, 0, ctx->stream>>>(st.p, Tm.p, 1);
+  DBuf<const double*> Tmp(ctx, 1);
+  const double* Tm_ptr = Tm.p;
+  ctx->upload_small(Tmp.p, &Tm_ptr, sizeof(Tm_ptr));
+  init_state_kernel<<<1, 32, 0, ctx->stream>>>(st.p, Tmp.p, 1);
   DBuf<double> d_acc(ctx, kAcc2);
   ctx->upload_small(d_acc.p, acc, sizeof(double) * kAcc2);
   IcpParams prm;

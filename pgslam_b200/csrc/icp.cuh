@@ -92,7 +92,27 @@ struct PreparedRef {
   DBuf<float4> normals_sorted;
   DBuf<int> inv_pos;              // original index -> sorted position, built on first use (knn > 1)
   bool has_normals = false;
-  double T_refIn_refMean[16];
+  // T_refIn_refMean (identity + the reference mean) stays on the device: 16 doubles at
+  // T_mean->p + T_mean_off, shared by the references prepared together
+  std::shared_ptr<DBuf<double>> T_mean;
+  size_t T_mean_off = 0;
+};
+
+// Where a batch's clouds come from.  fetch() makes the pairs [lo, hi) available on `ctx` and may
+// start asynchronous uploads; before_run() is called right before those pairs are registered
+// (the point where the compute stream joins the uploads).  A worker fetches its NEXT chunk before
+// it registers the current one, so uploads overlap the registration of the chunk before.
+struct FetchedPairs {
+  std::vector<std::unique_ptr<Cloud>> owned;  // uploaded for this chunk; freed with it
+  std::vector<const Cloud*> readings, references;
+};
+struct PairSource {
+  virtual ~PairSource() {}
+  virtual void fetch(Ctx* ctx, int lo, int hi, FetchedPairs& out) = 0;
+  virtual void before_run(Ctx* ctx, FetchedPairs& f) {
+    (void)ctx;
+    (void)f;
+  }
 };
 
 class IcpEngine {
@@ -104,6 +124,8 @@ class IcpEngine {
   // ICP::operator() on P independent pairs
   void run_batch(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
                  const double* T_inits, pgs_icp_result* results);
+  // the same for P pairs that `src` delivers chunk by chunk (host-resident clouds: BASELINE C4)
+  void run_batch_source(int P, PairSource& src, const double* T_inits, pgs_icp_result* results);
   // ICPSequence
   void set_map(const Cloud& map);
   bool has_map() const { return map_ != nullptr; }
@@ -112,6 +134,8 @@ class IcpEngine {
  private:
   void prepare_references(std::vector<std::unique_ptr<Cloud>>& refs, bool centre_first,
                           std::vector<std::unique_ptr<PreparedRef>>& out);
+  void run_direct(const std::vector<const Cloud*>& readings, const std::vector<const Cloud*>& references,
+                  const double* T_inits, pgs_icp_result* results);
   void run_prepared(const std::vector<const Cloud*>& readings, const std::vector<const PreparedRef*>& refs,
                     const double* T_inits, pgs_icp_result* results);
   IcpParams params_;

@@ -20,6 +20,7 @@ struct BuildJob {
   const float4* src;
   float4* dst;    // sorted points (n_leaves * kLeaf entries)
   float* nodes;   // 2*P*6 floats
+  float* cells;   // 2*P*6 floats
   int n, n_leaves, P, depth;
   const uint32_t* order;  // order[j] = original index of the j-th point in tree order
 };
@@ -156,6 +157,67 @@ __global__ void __launch_bounds__(1024) upper_levels_kernel(const BuildJob* __re
   }
 }
 
+// Exclusive cells, top-down.  cell(i) is an axis-aligned region that contains NO point of any
+// leaf outside node i's subtree: the root's cell is all of space, and a pair of siblings L, R
+// cuts their parent's cell along the axis a on which their point sets are best separated -
+// cell(L).hi[a] = min(.., box(R).lo[a]), cell(R).lo[a] = max(.., box(L).hi[a]) (or mirrored).
+// Every point of R has x_a >= box(R).lo[a], so none lies strictly inside cell(L), whether or
+// not the two boxes overlap (an overlap only makes the cell smaller than the box).  A search
+// whose candidate ball lies strictly inside cell(i) can therefore start at node i and never
+// has to look above it (match_persistent_kernel in icp.cu): the stored bounds are compared with
+// the same fp32 subtraction the distance uses, so the proof survives rounding (monotonicity).
+// Same {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z} layout as the boxes.
+__global__ void __launch_bounds__(1024) cell_levels_kernel(const BuildJob* __restrict__ jobs) {
+  const BuildJob job = jobs[blockIdx.x];
+  const float inf = __int_as_float(0x7f800000);
+  // position of lo[d] / hi[d] inside a 6-float record
+  const int LO[3] = {0, 1, 4}, HI[3] = {2, 3, 5};
+  if (threadIdx.x < 6) {
+    const bool is_lo = threadIdx.x == 0 || threadIdx.x == 1 || threadIdx.x == 4;
+    job.cells[6 + threadIdx.x] = is_lo ? -inf : inf;  // node 1 = root
+    job.cells[threadIdx.x] = is_lo ? -inf : inf;      // node 0 unused
+  }
+  __syncthreads();
+  for (int width = 1; width < job.P; width <<= 1) {
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+      const int node = width + i;
+      const float* bl = job.nodes + (size_t)(2 * node) * 6;
+      const float* br = bl + 6;
+      float cl[6], cr[6];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) cl[e] = cr[e] = job.cells[(size_t)node * 6 + e];
+      const bool both = bl[LO[0]] <= bl[HI[0]] && br[LO[0]] <= br[HI[0]];  // an empty box is (+inf, -inf)
+      if (both) {
+        float best = -inf;
+        int axis = 0;
+        bool l_below = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float sa = br[LO[d]] - bl[HI[d]];  // L below R along d
+          const float sb = bl[LO[d]] - br[HI[d]];  // R below L along d
+          if (sa > best) { best = sa; axis = d; l_below = true; }
+          if (sb > best) { best = sb; axis = d; l_below = false; }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (d != axis) continue;
+          if (l_below) {
+            cl[HI[d]] = fminf(cl[HI[d]], br[LO[d]]);
+            cr[LO[d]] = fmaxf(cr[LO[d]], bl[HI[d]]);
+          } else {
+            cl[LO[d]] = fmaxf(cl[LO[d]], br[HI[d]]);
+            cr[HI[d]] = fminf(cr[HI[d]], bl[LO[d]]);
+          }
+        }
+      }
+      float* ol = job.cells + (size_t)(2 * node) * 6;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { ol[e] = cl[e]; ol[6 + e] = cr[e]; }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std::vector<int>& n, int span,
@@ -183,7 +245,8 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
     while ((1 << idx->depth) < idx->P) ++idx->depth;
     idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
     idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
-    jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->n, idx->n_leaves, idx->P, idx->depth, nullptr};
+    if (want_boxes) idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
+    jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->cells.p, idx->n, idx->n_leaves, idx->P, idx->depth, nullptr};
     max_n = std::max(max_n, n[b]);
     max_P = std::max(max_P, idx->P);
     max_leaves = std::max(max_leaves, idx->n_leaves);
@@ -237,7 +300,8 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
   if (want_boxes) {
     leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
     upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-    ctx_count_launches(ctx, 2);
+    cell_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
+    ctx_count_launches(ctx, 3);
   }
   PGS_LAUNCH_CHECK();
 }
@@ -246,8 +310,10 @@ namespace {
 struct ShiftJob {
   const float4* src_pts;
   const float* src_nodes;
+  const float* src_cells;
   float4* dst_pts;
   float* dst_nodes;
+  float* dst_cells;
   int n_pts;    // n_leaves * kLeaf
   int n_nodes;  // 2 * P
 };
@@ -271,6 +337,12 @@ shift_index_kernel(const ShiftJob* __restrict__ jobs, const float* __restrict__ 
     // empty boxes (+inf / -inf) stay empty
     o[0] = __fsub_rn(a[0], sx); o[1] = __fsub_rn(a[1], sy); o[2] = __fsub_rn(a[2], sx);
     o[3] = __fsub_rn(a[3], sy); o[4] = __fsub_rn(a[4], sz); o[5] = __fsub_rn(a[5], sz);
+    // the cells' faces are point coordinates (or +-inf): the same monotone shift keeps every
+    // outside point outside
+    const float* ca = job.src_cells + (size_t)i * 6;
+    float* co = job.dst_cells + (size_t)i * 6;
+    co[0] = __fsub_rn(ca[0], sx); co[1] = __fsub_rn(ca[1], sy); co[2] = __fsub_rn(ca[2], sx);
+    co[3] = __fsub_rn(ca[3], sy); co[4] = __fsub_rn(ca[4], sz); co[5] = __fsub_rn(ca[5], sz);
   }
 }
 }  // namespace
@@ -287,7 +359,9 @@ void derive_shifted_indices(Ctx* ctx, const std::vector<const Index*>& src, cons
     idx->n = src[b]->n; idx->n_leaves = src[b]->n_leaves; idx->P = src[b]->P; idx->depth = src[b]->depth;
     idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
     idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
-    jobs[b] = ShiftJob{src[b]->pts.p, src[b]->nodes.p, idx->pts.p, idx->nodes.p, idx->n_leaves * kLeaf, 2 * idx->P};
+    idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
+    jobs[b] = ShiftJob{src[b]->pts.p, src[b]->nodes.p, src[b]->cells.p, idx->pts.p, idx->nodes.p, idx->cells.p,
+                       idx->n_leaves * kLeaf, 2 * idx->P};
     max_items = std::max(max_items, std::max(jobs[b].n_pts, jobs[b].n_nodes));
     out.push_back(std::move(idx));
   }

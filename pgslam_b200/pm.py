@@ -63,6 +63,12 @@ class IcpResult(C.Structure):
                 ("n_reading", C.c_int64), ("n_reference", C.c_int64)]
 
 
+class HostCloud(C.Structure):
+    """pgs_host_cloud: a host-resident DataPoints (features 4 x N column-major + descriptor blocks)."""
+    _fields_ = [("features4xN", C.c_void_p), ("n", C.c_int64), ("n_descriptors", C.c_int),
+                ("labels", C.POINTER(C.c_char_p)), ("spans", C.POINTER(C.c_int)), ("data", C.POINTER(C.c_void_p))]
+
+
 class StageTimes(C.Structure):
     _fields_ = [("filters_ms", C.c_float), ("index_ms", C.c_float), ("loop_ms", C.c_float),
                 ("total_ms", C.c_float), ("match_ms", C.c_float), ("select_ms", C.c_float),
@@ -121,6 +127,8 @@ SIGNATURES = {
     "pgs_icp_has_map": (C.c_int, [_vp]),
     "pgs_icp_run_sequence": (C.c_int, [_vp, _vp, _dp, C.POINTER(IcpResult)]),
     "pgs_icp_run_batch": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _dp, C.POINTER(IcpResult)]),
+    "pgs_icp_run_batch_multi": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.POINTER(HostCloud), C.POINTER(HostCloud),
+                                          _dp, C.c_int, C.POINTER(IcpResult)]),
     "pgs_icp_probe_overlap": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "pgs_icp_probe_residual": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "pgs_config_check": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
@@ -130,6 +138,7 @@ SIGNATURES = {
     "pgs_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "pgs_ctx_set_batch_streams": (C.c_int, [_vp, C.c_int]),
     "pgs_ctx_last_stage_times": (C.c_int, [_vp, C.POINTER(StageTimes)]),
+    "pgs_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
 }
 
 
@@ -218,6 +227,10 @@ class Context:
     def set_batch_streams(self, n: int):
         """Worker streams a batch of independent pairs is split over (default 4)."""
         self.check(self.lib.pgs_ctx_set_batch_streams(self.h, int(n)))
+
+    def set_option(self, key: str, value):
+        """Scheduling knobs of the hot kernels (pgs_ctx_set_option); results never depend on them."""
+        self.check(self.lib.pgs_ctx_set_option(self.h, key.encode(), float(value)))
 
     def stage_times(self) -> dict:
         t = StageTimes()
@@ -656,6 +669,22 @@ class ICP:
         self.ctx.check(st)
         return out
 
+    def compute_batch_array(self, readings, references, T_inits=None, handles=None) -> np.ndarray:
+        """compute_batch without per-pair Python objects: returns the pgs_icp_result records as one
+        structured numpy array (fields T [col-major 16], covariance, iterations, status, ...).
+        `handles` = (reading handle array, reference handle array) from batch_handles(), reusable."""
+        ra, fa = handles if handles is not None else batch_handles(readings, references)
+        P = len(ra)
+        Tp = None
+        if T_inits is not None:
+            Tflat = np.ascontiguousarray(np.concatenate([_mat(t).ravel(order="F") for t in T_inits]))
+            Tp = Tflat.ctypes.data_as(_dp)
+        res = (IcpResult * P)()
+        st = self.ctx.lib.pgs_icp_run_batch(self.h, P, ra, fa, Tp, res)
+        out = np.frombuffer(res, dtype=np.dtype(IcpResult)).copy()
+        self.ctx.check(st)
+        return out
+
     def probe_overlap(self, reading, reference, T) -> float:
         """Localizer::ComputeOverlapWith (Localizer.hpp:282-348), one fused call."""
         T = _mat(T)
@@ -676,6 +705,60 @@ class ICP:
                 self.ctx.lib.pgs_icp_destroy(self.h)
         except Exception:
             pass
+
+
+def batch_handles(readings, references):
+    """ctypes handle arrays for compute_batch_array (build once, reuse every call)."""
+    P = len(readings)
+    return (_vp * P)(*[c.h for c in readings]), (_vp * P)(*[c.h for c in references])
+
+
+def host_clouds(arrays, descriptors=None):
+    """pgs_host_cloud array over host buffers.  `arrays`: (N, 4) float32 C-contiguous numpy arrays
+    ({x,y,z,1} per point: PM's column-major 4 x N), or (pointer, n) tuples for raw (e.g. pinned)
+    memory.  `descriptors`: optional list of {label: (N, span) float32 array}.  The returned
+    object keeps every buffer alive."""
+    P = len(arrays)
+    out = (HostCloud * P)()
+    keep = [out]
+    for i, a in enumerate(arrays):
+        if isinstance(a, tuple):
+            ptr, n = a
+        else:
+            if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] != 4 or not a.flags["C_CONTIGUOUS"]:
+                raise InvalidField(INVALID_FIELD, "host clouds must be (N, 4) float32 C-contiguous")
+            keep.append(a)
+            ptr, n = a.ctypes.data, a.shape[0]
+        out[i].features4xN = ptr
+        out[i].n = n
+        d = (descriptors[i] if descriptors else None) or {}
+        out[i].n_descriptors = len(d)
+        if d:
+            labels = (C.c_char_p * len(d))(*[k.encode() for k in d])
+            blocks = [np.ascontiguousarray(v, dtype=np.float32) for v in d.values()]
+            spans = (C.c_int * len(d))(*[(b.shape[1] if b.ndim == 2 else 1) for b in blocks])
+            data = (C.c_void_p * len(d))(*[b.ctypes.data for b in blocks])
+            out[i].labels, out[i].spans, out[i].data = labels, spans, data
+            keep += [labels, blocks, spans, data]
+    out._keep = keep
+    return out
+
+
+def compute_batch_multi(icps, readings, references, T_inits=None, pinned=False) -> np.ndarray:
+    """pgs_icp_run_batch_multi: host-resident pairs registered on the contexts of `icps` (one ICP
+    object per GPU, same chain), contiguous-block sharded; returns the pgs_icp_result records as
+    a structured numpy array in pair order.  `readings` / `references`: host_clouds(...) arrays."""
+    P = len(readings)
+    hs = (_vp * len(icps))(*[i.h for i in icps])
+    Tp = None
+    if T_inits is not None:
+        Tflat = np.ascontiguousarray(np.concatenate([_mat(t).ravel(order="F") for t in T_inits]))
+        Tp = Tflat.ctypes.data_as(_dp)
+    res = (IcpResult * max(P, 1))()
+    st = icps[0].ctx.lib.pgs_icp_run_batch_multi(hs, len(icps), P, readings, references, Tp, int(bool(pinned)), res)
+    out = np.frombuffer(res, dtype=np.dtype(IcpResult)).copy()[:P]
+    icps[0].ctx.check(st)
+    return out
 
 
 class ICPSequence(ICP):

@@ -1009,3 +1009,57 @@ def test_icp_point_to_plane_forced_modes(pm, pair30k, mode):
     Tm = e.compute(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": oref.desc("normals")}), w, pm.Matches(ids, d2))
     np.testing.assert_allclose(Tm, ref_out["T"], rtol=0, atol=1e-11)
     assert e._last.residual == pytest.approx(ref_out["residual"], rel=1e-11)
+
+
+# ------------------------------------------------ matcher scheduling variants ---
+def _bits(res):
+    keys = ("T", "covariance", "iterations", "status", "overlap", "weighted_point_used_ratio", "point_used_ratio",
+            "residual", "n_reading", "n_reference")
+    return [np.asarray(res[k]).tobytes() for k in keys]
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_match_modes_give_bit_identical_registrations(pm, ctx, pair30k, mode):
+    """The cell-guided and persistent matchers (pgs_ctx_set_option "match_mode") must return the
+    same exact nearest neighbours as the default one: whole results compared bit for bit."""
+    cases = [(util.C1, pair30k[0], pair30k[1])]
+    rd, rf, _ = synth.scan_pair(2, beams=64, az_steps=1875)
+    cases.append((util.C2, rd, rf))
+    g = np.random.default_rng(7)
+    for n_ref, n_rd in ((1, 5), (7, 7), (9, 40), (17, 33), (100, 3), (1000, 900)):
+        a = np.ones((4, n_ref), np.float32); a[:3] = g.uniform(-2, 2, (3, n_ref))
+        b = np.ones((4, n_rd), np.float32); b[:3] = g.uniform(-2, 2, (3, n_rd))
+        cases.append((util.C1, b, a))
+    try:
+        for cfg, rd, rf in cases:
+            out = {}
+            for m in (0, mode):
+                ctx.set_option("match_mode", m)
+                icp = pm.ICP()
+                icp.loadFromYaml(util.to_yaml(cfg))
+                try:
+                    icp(pm.DataPoints(rd), pm.DataPoints(rf))
+                except pm.PointMatcherError:
+                    pass
+                out[m] = icp.last
+            assert _bits(out[0]) == _bits(out[mode]), (mode, rd.shape, rf.shape, out[0]["iterations"], out[mode]["iterations"])
+    finally:
+        ctx.set_option("match_mode", 0)
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_match_modes_batch_with_ragged_pairs(pm, ctx, mode):
+    """A batch of pairs of different sizes through the persistent matcher: ranges of inactive /
+    short pairs are skipped, results equal the default matcher's bit for bit."""
+    pairs = [synth.scan_pair(20 + i, beams=8 + 4 * i, az_steps=300 + 50 * i)[:2] for i in range(6)]
+    try:
+        out = {}
+        for m in (0, mode):
+            ctx.set_option("match_mode", m)
+            icp = pm.ICP()
+            icp.loadFromYaml(util.to_yaml(util.C2))
+            out[m] = icp.compute_batch([pm.DataPoints(r) for r, _ in pairs], [pm.DataPoints(f) for _, f in pairs])
+        for a, b in zip(out[0], out[mode]):
+            assert _bits(a) == _bits(b)
+    finally:
+        ctx.set_option("match_mode", 0)
