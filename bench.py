@@ -1,29 +1,34 @@
 #!/usr/bin/env python
 """bench.py — ICP registrations/s on 120k-point scan pairs (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] — synthetic 64-beam
-120 000-point scan pair, point-to-plane ICP with the SurfaceNormal(knn=10)
-reference filter, KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, Counter(40) +
-Differential checkers.  One "step" = one pass of the whole registration path
-(reference filter -> index build -> ICP loop -> result) over one batch of
-`--pairs` distinct pairs per GPU; pairs are independent, so N GPUs each take
-their own batch (weak scaling) and only the per-pair 4x4 results are gathered
+Workload (config.workload): every registration is BASELINE.json configs[1] — synthetic 64-beam
+120 000-point scan pair, point-to-plane ICP with the SurfaceNormal(knn=10) reference filter,
+KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, Counter(40) + Differential checkers — and the batch
+is configs[3]: a fixed pool of `--pool` (4096) DISTINCT candidate pairs, cut into contiguous
+blocks over the N GPUs (pgslam_b200/dist.py shard_range; strong scaling, no data-path
+collective).  One "step" = every rank registers its whole block (reference filter -> index
+build -> ICP loop -> result) and the per-pair result records are gathered to every rank
 (NCCL all_gather), inside the timed region.
 
-  value : registrations/s with the clouds already resident in HBM
-  e2e   : the same through the public API from pinned HOST buffers (H2D of
-          both clouds and D2H of the result inside the timed region)
-  roofline : the dominant kernel (match = fused transform + exact kNN), against
-          the measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (a port of the libpointmatcher/libnabo path) on
-          this box's host cores, same workload, bounded sample
+  value : registrations/s with the clouds already resident in HBM (pgs_icp_run_batch)
+  e2e   : the same through the host-memory entry pgs_icp_run_batch_multi from PINNED HOST buffers
+          (H2D of both clouds of every pair and D2H of the results inside the timed region)
+  roofline : the dominant kernel (match = fused transform + exact kNN), against the measured HBM
+          copy bandwidth in MEASURED_PEAKS.json
+  bench_parity : >= 16 pairs of the pool re-registered by the CPU oracle inside the run
+          (iterations equal, pose deltas); results_sha256 = hash of all gathered records, equal at
+          every N because a pair's result does not depend on how the pool is cut
+  cpu_baseline : the CPU oracle (a port of the libpointmatcher/libnabo path) on this box's host
+          cores (all threads, and one thread), same workload, bounded sample
+  c3 / c5 / dropin_ms : the other BASELINE configs and the C++ drop-in call sites (N = 1 only)
 
-`--impl reference` times that CPU path alone (the reference's libpointmatcher
-cannot be built here: un-vendored, un-pinned, absent — DESIGN.md).
+`--impl reference` times that CPU path alone (the reference's libpointmatcher cannot be built
+here: un-vendored, un-pinned, absent — DESIGN.md).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -40,8 +45,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "icp_registrations_per_s_120k_pt_pairs"
 UNIT = "registrations/s"
-WORKLOAD = ("C2: synthetic 64-beam 120000-pt scan pair, point-to-plane ICP, SurfaceNormal(knn=10) reference "
-            "filter, KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, Counter(40)+Differential(1e-3,1e-3,3)")
+WORKLOAD = ("C2 registrations drawn from the C4 pool: synthetic 64-beam 120000-pt scan pairs, point-to-plane ICP, "
+            "SurfaceNormal(knn=10) reference filter, KDTreeMatcher k=1 eps=0, TrimmedDist 0.85, "
+            "Counter(40)+Differential(1e-3,1e-3,3); fixed pool of distinct candidate pairs sharded over the GPUs")
+BEAMS, AZ = 64, 1875
 
 
 def c2_config():
@@ -51,12 +58,12 @@ def c2_config():
 
 def gen_pair(seed):
     from pgslam_b200 import synth
-    rd, rf, _ = synth.scan_pair(seed, beams=64, az_steps=1875)
+    rd, rf, _ = synth.scan_pair(seed, beams=BEAMS, az_steps=AZ)
     return rd, rf
 
 
 def gen_pairs(seeds):
-    """Distinct synthetic pairs; generated in parallel on the host cores."""
+    """Distinct synthetic pairs from the numpy generator; in parallel on the host cores."""
     seeds = list(seeds)
     if len(seeds) <= 2:
         return [gen_pair(s) for s in seeds]
@@ -80,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,7 +106,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -108,13 +115,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for nme, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def peaks():
@@ -125,14 +133,14 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(steps, warmup, sample_pairs=1):
-    """The CPU path (oracle port) on all host threads: one registration per step."""
+def cpu_reference_run(steps, warmup, sample_pairs=1, threads=None):
+    """The CPU path (oracle port): one registration per step, OpenMP over queries."""
     from oracle import binding as ob
     cfg = ob.config_from_dict(c2_config())
     pairs = gen_pairs(range(1000, 1000 + sample_pairs))
     clouds = [(ob.Cloud(rd), ob.Cloud(rf)) for rd, rf in pairs]
     # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to its workers)
-    ob.lib().orc_set_num_threads(os.cpu_count() or 1)
+    ob.lib().orc_set_num_threads(threads or os.cpu_count() or 1)
     threads = ob.lib().orc_num_threads()
     its = []
     for i in range(warmup):
@@ -144,13 +152,95 @@ def cpu_reference_run(steps, warmup, sample_pairs=1):
     dt = time.perf_counter() - t0
     return dict(value=steps / dt, seconds=dt, cores=threads, iterations=its,
                 sample=f"{steps} registration(s) of the same C2 workload ({len(clouds)} distinct pair(s)), "
-                       f"OpenMP over queries on {threads} host thread(s)")
+                       f"OpenMP over queries on {threads} host thread(s); about 0.14 s of each registration is "
+                       f"serial (copies, quantile, minimizer)")
 
 
 def emit(line: dict, fd: int):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
 
+# ------------------------------------------------------------------------------------------------
+def leg_c3(pm, ctx, util, scans=200):
+    """BASELINE C3 in the small: sequential scan-to-map odometry through ICPSequence
+    (Localizer.hpp:103-126,148,254): every scan uploaded from the host, input filters, registration
+    against a 3-keyframe local map seeded with the previous pose, a new keyframe (local map rebuilt
+    on the device, setMap) every 10 scans.  One sequence is sequential: one GPU."""
+    from pgslam_b200 import synth
+    poses = synth.trajectory(scans + 1, step=0.25, turn_deg=1.0)
+    scene = synth.make_scene(77)
+    host = [np.ascontiguousarray(synth.velodyne_scan(77, 10 + i, poses[i], BEAMS, AZ, scene=scene).T) for i in range(24)]
+    filt = pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS), ctx=ctx)
+    seq = pm.ICPSequence(ctx)
+    seq.loadFromYaml(util.to_yaml(util.C2))
+    rigid = pm.RigidTransformation(ctx)
+
+    def cloud(i):
+        c = pm.DataPoints(np.asfortranarray(host[i % len(host)].T), ctx=ctx)
+        filt.apply(c)
+        return c
+    keyframes = [(cloud(0), np.eye(4))]
+    seq.setMap(keyframes[0][0])
+    T = np.eye(4)
+    lat, its = [], []
+    t_all = time.perf_counter()
+    for i in range(1, scans + 1):
+        t0 = time.perf_counter()
+        c = cloud(i % len(host))
+        try:
+            T = seq(c, T)
+        except pm.PointMatcherError:
+            T = np.eye(4)
+        its.append(seq.last["iterations"])
+        if i % 10 == 0:  # keyframe: local map = last 3 keyframes in the newest one's frame
+            keyframes.append((c, T.copy()))
+            keyframes = keyframes[-3:]
+            Tn = np.linalg.inv(keyframes[-1][1])
+            m = pm.assemble_local_map([keyframes[-1][0]] + [k for k, _ in keyframes[:-1]],
+                                      [np.eye(4)] + [Tn @ Tk for _, Tk in keyframes[:-1]])
+            seq.setMap(m)
+            T = np.eye(4)
+        lat.append(1e3 * (time.perf_counter() - t0))
+    dt = time.perf_counter() - t_all
+    lat.sort()
+    return {"scans": scans, "scans_per_s": scans / dt, "latency_ms_p50": lat[len(lat) // 2],
+            "latency_ms_p99": lat[min(len(lat) - 1, int(0.99 * len(lat)))], "iterations_mean": statistics.mean(its),
+            "note": "120k-pt scans from host memory, input filters (SurfaceNormal knn=10 + 3 more), ICPSequence against a "
+                    "local map of up to 3 keyframes (360k pts), keyframe + setMap every 10 scans"}
+
+
+def leg_c5(pm, ctx, util, reps=5):
+    """BASELINE C5: dense 1M-point scan-to-map registration, voxel-subsampled reading, trimmed 0.75."""
+    from pgslam_b200 import synth
+    rd, rf, _ = synth.scan_pair(9, beams=128, az_steps=7813)  # 1 000 064 points
+    icp = pm.ICP(ctx)
+    icp.loadFromYaml(util.to_yaml(util.C5))
+    a, b = pm.DataPoints(rd, ctx=ctx), pm.DataPoints(rf, ctx=ctx)
+    icp(a, b)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        icp(a, b)
+    dt = (time.perf_counter() - t0) / reps
+    return {"points": int(rd.shape[1]), "ms_per_registration": 1e3 * dt, "registrations_per_s": 1.0 / dt,
+            "iterations": icp.last["iterations"], "n_reading_after_voxel_filter": icp.last["n_reading"]}
+
+
+def leg_dropin():
+    """pgslam's own call sites (LoopCloser::ProcessVertex + CheckIcpResult + ComputeResidualError,
+    Localizer::ComputeOverlapWith) compiled against the C++ adapter, timed end to end at 120k points."""
+    try:
+        from tests.test_cpp_adapter import build_callsites
+        exe = build_callsites()
+        out = subprocess.run([exe, "--bench", "120000"], capture_output=True, text=True, timeout=300)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (out.stdout + out.stderr)[-300:]}
+    except Exception as e:  # the adapter bench is an extra: never fail the bench line for it
+        return {"error": repr(e)[:300]}
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     # exactly ONE line may reach stdout: native libraries (NCCL prints its version)
     # write to fd 1 behind Python's back, so fd 1 is pointed at stderr for the
@@ -163,11 +253,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=96, help="distinct pairs per GPU per step")
+    ap.add_argument("--pool", type=int, default=4096, help="distinct candidate pairs in the job (BASELINE C4)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="registrations for the cpu_baseline leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch-streams", type=int, default=4,
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C5 / drop-in legs")
+    ap.add_argument("--parity-pairs", type=int, default=16)
+    ap.add_argument("--batch-streams", type=int, default=8,
                     help="worker streams the library splits a batch over (pgs_ctx_set_batch_streams)")
+    ap.add_argument("--batch-chunk", type=int, default=12, help="pairs per chunk a worker pulls")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -182,9 +275,10 @@ def main():
         r = cpu_reference_run(max(args.steps, 1), args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 points / f64 reductions",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 points / f64 reductions",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "points_per_scan": 120000},
+                "config": {"workload": WORKLOAD, "pool_pairs": args.pool, "points_per_scan": BEAMS * AZ,
+                           "step": "one registration of the workload per step (bounded sample of the pool)"},
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "iterations": r["iterations"]}
@@ -194,78 +288,70 @@ def main():
     # --------------------------------------------------------------------- ours
     import torch
     import torch.distributed as dist
-    from pgslam_b200 import build, pm
+    from pgslam_b200 import build, pm, synth_torch
+    from pgslam_b200 import dist as pdist
     from tests import util
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     build.build()
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     multi = world > 1
     if multi:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     ctx = pm.Context(local_rank, stream.cuda_stream)
     ctx.set_batch_streams(args.batch_streams)
+    ctx.set_option("batch_chunk", args.batch_chunk)
     icp = pm.ICP(ctx)
     icp.loadFromYaml(util.to_yaml(c2_config()))
 
-    B = args.pairs
-    pairs = gen_pairs(range(rank * B, rank * B + B))
-    n_pts = pairs[0][0].shape[1]
-    in_bytes = sum(rd.nbytes + rf.nbytes for rd, rf in pairs)
-    # pinned host copies for the e2e leg (point-major float32, exactly what the ABI takes)
-    host = [(torch.from_numpy(np.ascontiguousarray(rd.T)).pin_memory(), torch.from_numpy(np.ascontiguousarray(rf.T)).pin_memory())
-            for rd, rf in pairs]
-    dev_rd = [pm.DataPoints(ctx=ctx, device_ptr=None, features=rd) for rd, _ in pairs]
-    dev_rf = [pm.DataPoints(ctx=ctx, device_ptr=None, features=rf) for _, rf in pairs]
+    # ---- the pool: this rank's contiguous block, generated on the device, pair i <- seed i ----------
+    POOL = args.pool
+    mine = pdist.shard_range(POOL, rank, world)
+    B = len(mine)
+    n_pts = BEAMS * AZ
+    t_setup = time.perf_counter()
+    host = torch.empty((max(B, 1), 2, n_pts, 4), dtype=torch.float32).pin_memory()  # e2e leg: pinned host copies
+    dev_rd, dev_rf = [], []
+    for c0 in range(0, B, 32):
+        seeds = [mine[j] for j in range(c0, min(B, c0 + 32))]
+        data, _ = synth_torch.scan_pairs(seeds, dev, beams=BEAMS, az_steps=AZ)
+        for j, (rd, rf) in enumerate(data):
+            dev_rd.append(pm.DataPoints(ctx=ctx, device_ptr=rd.data_ptr(), n=n_pts))
+            dev_rf.append(pm.DataPoints(ctx=ctx, device_ptr=rf.data_ptr(), n=n_pts))
+            host[c0 + j, 0].copy_(rd, non_blocking=True)
+            host[c0 + j, 1].copy_(rf, non_blocking=True)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        del data
+    torch.cuda.empty_cache()
+    handles = pm.batch_handles(dev_rd, dev_rf)
+    host_rd = pm.host_clouds([(host[j, 0].data_ptr(), n_pts) for j in range(B)])
+    host_rf = pm.host_clouds([(host[j, 1].data_ptr(), n_pts) for j in range(B)])
+    in_bytes = 2 * B * n_pts * 16
+    setup_s = time.perf_counter() - t_setup
 
-    gathered = torch.empty((world * B, 16), dtype=torch.float64, device="cuda") if multi else None
+    def gather(rec):
+        """the path's only exchange step: per-pair result records to every rank (pair order)"""
+        return pdist.gather_records(rec, POOL, dev if multi else None)
 
-    def gather(results):
-        """the path's only exchange step: per-pair transforms to every rank"""
-        if not multi:
-            return
-        loc = torch.tensor(np.stack([r["T"].ravel(order="F") for r in results]), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(gathered, loc)
-
-    resident_wall = []  # host wall-clock of every device-resident step (warm-up included)
+    resident_wall, e2e_wall = [], []
 
     def step_resident():
         t0 = time.perf_counter()
-        res = icp.compute_batch(dev_rd, dev_rf)
-        gather(res)
+        rec = icp.compute_batch_array(dev_rd, dev_rf, handles=handles) if B else pm.empty_records()
+        allrec = gather(rec)
         resident_wall.append(round(1e3 * (time.perf_counter() - t0), 2))
-        return res
-
-    def upload():
-        """H2D of one step's inputs: 2 x B clouds from pinned host memory, asynchronous on the
-        library's copy stream (public API: DataPoints(pinned_host_ptr=...))."""
-        rds = [pm.DataPoints(ctx=ctx, pinned_host_ptr=hrd.data_ptr(), n=hrd.shape[0]) for hrd, _ in host]
-        rfs = [pm.DataPoints(ctx=ctx, pinned_host_ptr=hrf.data_ptr(), n=hrf.shape[0]) for _, hrf in host]
-        return rds, rfs
-
-    pending = []
-    e2e_wall = []  # host wall-clock of every e2e step (warm-up included), for the record
-    from concurrent.futures import ThreadPoolExecutor
-    uploader = ThreadPoolExecutor(max_workers=1)
+        return rec, allrec
 
     def step_e2e():
-        # software pipeline: this step's inputs were queued on the copy stream while the previous
-        # step computed, and the next step's are queued by a helper thread while this one computes
-        # (pinned uploads touch only the library's copy stream); every step still uploads its own
-        # inputs and downloads its own results
         t0 = time.perf_counter()
-        rds, rfs = pending.pop().result() if pending else upload()
-        t1 = time.perf_counter()
-        pending.append(uploader.submit(upload))
-        res = icp.compute_batch(rds, rfs)
-        gather(res)
+        rec = pm.compute_batch_multi([icp], host_rd, host_rf, pinned=True) if B else pm.empty_records()
+        allrec = gather(rec)
         e2e_wall.append(round(1e3 * (time.perf_counter() - t0), 2))
-        if os.environ.get("BENCH_TRACE_E2E"):
-            sys.stderr.write("e2e step: waited %.1f ms for the upload calls, compute_batch %.1f ms\n"
-                             % (1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
-        return res
+        return rec, allrec
 
     def barrier():
         if multi:
@@ -288,110 +374,156 @@ def main():
             ms = float(t.item())
         return ms, out
 
-    # a generation-2 Python garbage collection in a process that has imported torch takes ~35 ms
-    # (measured: one e2e step in ~15 doubled); the steps allocate nothing cyclic, so the
-    # collector is parked for the measurement instead of being timed
+    # a generation-2 Python garbage collection in a process that has imported torch takes ~35 ms;
+    # the steps allocate nothing cyclic, so the collector is parked for the measurement
     import gc
     gc.collect()
     gc.freeze()
     gc.disable()
 
-    # clocks are sampled from the warm-up steps on (same load as the timed steps): the
-    # timed region alone is ~100 ms, too short for more than a sample or two
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     for _ in range(args.warmup):
         step_resident()
     launches0 = ctx.launch_count
-    ms, res = timed(step_resident, args.steps)
+    ms, (rec, allrec) = timed(step_resident, args.steps)
     launches = ctx.launch_count - launches0
-    # per-kernel CUDA-event timings of one more identical step, taken with the batch on ONE
-    # stream: with the sub-batches overlapping on several streams an event pair around a kernel
-    # would also time whatever the other streams run in between
-    ctx.set_profiling(True)
-    step_resident()
-    stage = ctx.stage_times()
-    ctx.set_profiling(False)
-    clocks = sampler.stop() if rank == 0 else None
 
     for _ in range(args.warmup):
         step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, (rec_e2e, allrec_e2e) = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
-    if pending:
-        pending.pop().result()  # drain the pipeline before the latency measurement
-    uploader.shutdown()
-
-    # single-pair latency (batch of 1), for the record
-    one_rd, one_rf = [dev_rd[0]], [dev_rf[0]]
-    for _ in range(3):
-        icp.compute_batch(one_rd, one_rf)
-    ms_one, _ = timed(lambda: icp.compute_batch(one_rd, one_rf), 10)
+    # per-kernel CUDA-event timings of one 96-pair batch, taken on ONE stream: with chunks
+    # overlapping on several streams an event pair around a kernel would also time whatever
+    # the other streams run in between
+    nprof = min(96, B)
+    stage = None
+    prof_rec = None
+    if nprof:
+        ctx.set_profiling(True)
+        prof_rec = icp.compute_batch_array(dev_rd[:nprof], dev_rf[:nprof])
+        stage = ctx.stage_times()
+        ctx.set_profiling(False)
+        # single-pair latency (batch of 1), for the record
+        for _ in range(3):
+            icp.compute_batch_array(dev_rd[:1], dev_rf[:1])
+        ms_one, _ = timed(lambda: icp.compute_batch_array(dev_rd[:1], dev_rf[:1]), 10)
+    else:
+        ms_one = 0.0
+        timed(lambda: None, 1)
 
     if rank != 0:
         if multi:
             dist.destroy_process_group()
         return
 
-    total_pairs = world * B
-    value = total_pairs * args.steps / (ms / 1e3)
-    e2e_value = total_pairs * args.steps / (ms_e2e / 1e3)
-    iters = [r["iterations"] for r in res]
-    ok = sum(r["status"] == 0 for r in res)
-    # roofline of the dominant kernel (match): algorithmic bytes = per query 16 B
-    # read + 8 B match written, plus one pass over the reference (16 B/pt) per
-    # launch and pair; only pairs still iterating do work.
-    n_ref = res[0]["n_reference"]
-    alg_bytes = sum(r["iterations"] * (24.0 * r["n_reading"] + 16.0 * r["n_reference"]) for r in res)
-    match_s = stage["match_ms"] / 1e3
+    value = POOL * args.steps / (ms / 1e3)
+    e2e_value = POOL * args.steps / (ms_e2e / 1e3)
+    ok = int((allrec[:, 53] == 0).sum())
+    iters = allrec[:, 52]
+    sha = hashlib.sha256(np.ascontiguousarray(allrec).tobytes()).hexdigest()
+
+    # ---- in-run parity: pairs of this rank's block re-registered by the CPU oracle -------------------
+    parity = None
+    if args.parity_pairs > 0 and B:
+        from oracle import binding as ob
+        ob.lib().orc_set_num_threads(os.cpu_count() or 1)
+        cfg = ob.config_from_dict(c2_config())
+        pick = sorted(set(int(x) for x in np.linspace(0, B - 1, min(args.parity_pairs, B))))
+        max_dt = max_dr = 0.0
+        it_equal = 0
+        worst = None
+        for j in pick:
+            rd = np.asfortranarray(host[j, 0].numpy().T)
+            rf = np.asfortranarray(host[j, 1].numpy().T)
+            want = ob.icp_run(cfg, ob.Cloud(rd), ob.Cloud(rf))
+            got_T = rec[j]["T"].reshape(4, 4).T
+            dt = float(np.abs(got_T[:3, 3] - want["T"][:3, 3]).max())
+            dr = util.rot_angle(got_T, want["T"])
+            it_equal += int(int(rec[j]["iterations"]) == int(want["iterations"]))
+            if dt >= max_dt:
+                worst = int(mine[j])
+            max_dt, max_dr = max(max_dt, dt), max(max_dr, dr)
+        parity = {"pairs_checked": len(pick), "pool_indices": [int(mine[j]) for j in pick], "iterations_equal": it_equal,
+                  "max_dT_m": max_dt, "max_dR_rad": max_dr, "worst_pair": worst, "tolerance": "1e-5 m / 1e-5 rad, equal iteration counts",
+                  "ok": bool(it_equal == len(pick) and max_dt <= 1e-5 and max_dr <= 1e-5),
+                  "checker": "oracle/ (CPU port), same arrays the GPU registered"}
+
+    # ---- roofline of the dominant kernel (match): algorithmic bytes = per query 16 B read + 8 B match
+    # written, plus one pass over the reference (16 B/pt) per launch and pair
     peak, peak_src = peaks()
-    achieved = alg_bytes / match_s / 1e9 if match_s > 0 else 0.0
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture,
-    # valid only for the batch size it was captured at
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_match_kernel_ncu_full.json")) as f:
-            cap = json.load(f)
-        if cap.get("pairs") == B:
-            traffic = cap["dram_traffic_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "match_kernel (fused rigid transform + exact k=1 NN traversal)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch_all_pairs_active": sum(24.0 * r["n_reading"] + 16.0 * r["n_reference"] for r in res),
-                "peak_source": peak_src, "launches": stage["iterations_launched"],
-                "avg_launch_ms": stage["match_ms"] / max(stage["iterations_launched"], 1),
-                "algorithmic_bytes_per_step": alg_bytes,
-                "timing": "CUDA events around every launch of one extra step after the timed region, whole batch on one stream",
-                "stage_ms_last_step": {k: round(float(v), 3) for k, v in stage.items()}}
-    # the metric's second figure: exact nearest-neighbour queries answered per second by the
-    # matcher kernel alone (every launch answers one query per reading point of an active pair)
-    knn_qps = sum(r["iterations"] * r["n_reading"] for r in res) / match_s if match_s > 0 else 0.0
-    reg_bytes = 68.0 * n_ref + 32.0 * n_pts + statistics.mean(iters) * ((32 + 32 * 0.85) * n_pts + 16.0 * n_ref)
-    roofline["whole_registration"] = {"algorithmic_bytes": reg_bytes, "achieved_gbs": reg_bytes * value / world / 1e9,
-                                      "frac": reg_bytes * value / world / 1e9 / peak}
+    roofline = None
+    if stage:
+        alg_bytes = float(sum(int(r["iterations"]) * (24.0 * int(r["n_reading"]) + 16.0 * int(r["n_reference"])) for r in prof_rec))
+        per_launch_all = float(sum(24.0 * int(r["n_reading"]) + 16.0 * int(r["n_reference"]) for r in prof_rec))
+        match_s = stage["match_ms"] / 1e3
+        achieved = alg_bytes / match_s / 1e9 if match_s > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_match_kernel_ncu_full.json")) as f:
+                cap = json.load(f)
+            if cap.get("pairs") == nprof:
+                traffic = cap["dram_traffic_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": "match_kernel (fused rigid transform + exact k=1 NN traversal)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch_all_pairs_active": per_launch_all,
+                    "peak_source": peak_src, "launches": stage["iterations_launched"], "pairs_in_profiled_batch": nprof,
+                    "avg_launch_ms": stage["match_ms"] / max(stage["iterations_launched"], 1),
+                    "algorithmic_bytes_per_step": alg_bytes,
+                    "timing": "CUDA events around every launch of one 96-pair batch after the timed region, whole batch on one stream",
+                    "stage_ms_profiled_batch": {k: round(float(v), 3) for k, v in stage.items()}}
+        n_ref = int(prof_rec[0]["n_reference"])
+        reg_bytes = 68.0 * n_ref + 32.0 * n_pts + float(iters.mean()) * ((32 + 32 * 0.85) * n_pts + 16.0 * n_ref)
+        roofline["whole_registration"] = {"algorithmic_bytes": reg_bytes, "achieved_gbs": reg_bytes * value / world / 1e9,
+                                          "frac": reg_bytes * value / world / 1e9 / peak}
+        knn_qps = float(sum(int(r["iterations"]) * int(r["n_reading"]) for r in prof_rec)) / match_s if match_s > 0 else 0.0
+    else:
+        knn_qps = 0.0
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
-        n = args.cpu_steps or 64  # ~10 s of CPU work on this class of host
-        r = cpu_reference_run(n, 1, sample_pairs=min(4, n))
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    extras = {}
+    if world == 1:
+        if not args.no_cpu_baseline:  # reported on rank 0 at N = 1 only
+            n = args.cpu_steps or 64  # ~10 s of CPU work on this class of host
+            r = cpu_reference_run(n, 1, sample_pairs=min(4, n))
+            r1 = cpu_reference_run(4, 1, sample_pairs=1, threads=1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                   "one_thread": {"value": r1["value"], "cores": 1, "sample": r1["sample"]}}
+        if not args.no_extras:
+            for name, fn in (("c3", lambda: leg_c3(pm, ctx, util)), ("c5", lambda: leg_c5(pm, ctx, util)), ("dropin", leg_dropin)):
+                try:
+                    extras[name] = fn()
+                except Exception as e:  # extras never cost the headline line
+                    extras[name] = {"error": repr(e)[:300]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 points / f64 reductions", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "points_per_scan": n_pts,
-                       "batch_streams": args.batch_streams,
+            "config": {"workload": WORKLOAD, "pool_pairs": POOL, "pairs_per_gpu_per_step": len(pdist.shard_range(POOL, 0, world)),
+                       "points_per_scan": n_pts, "batch_streams": args.batch_streams, "batch_chunk": args.batch_chunk,
                        "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
-                       "parallelism": f"{world} GPU(s), independent pairs per rank, NCCL all_gather of 4x4 results"},
+                       "parallelism": f"{world} GPU(s), contiguous blocks of the pool per rank, NCCL all_gather of the result records",
+                       "pool_generator": "pgslam_b200/synth_torch.py on the device, pair i <- seed i"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
-                    "d2h_bytes_per_step": int(total_pairs * 480), "ms_per_step": ms_e2e / args.steps,
+                    "d2h_bytes_per_step": int(POOL * 480), "ms_per_step": ms_e2e / args.steps,
+                    "entry": "pgs_icp_run_batch_multi (host-resident pairs, pinned), chunked uploads inside the call",
+                    "results_equal_resident": bool(np.array_equal(allrec, allrec_e2e)),
                     "wall_ms_each_step_incl_warmup": e2e_wall},
-            "resident_wall_ms_each_step_incl_warmup": resident_wall[:args.warmup + args.steps],
+            "resident_wall_ms_each_step_incl_warmup": resident_wall,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "knn_queries_per_s": knn_qps, "iterations_mean": statistics.mean(iters), "pairs_ok": ok,
-            "single_pair_latency_ms": ms_one / 10.0}
+            "bench_parity": parity, "results_sha256": sha, "knn_queries_per_s": knn_qps,
+            "iterations_mean": float(iters.mean()), "pairs_ok": ok, "single_pair_latency_ms": ms_one / 10.0,
+            "setup_s": round(setup_s, 1)}
+    if extras:
+        line["c3"] = extras.get("c3")
+        line["c5"] = extras.get("c5")
+        dp = extras.get("dropin") or {}
+        line["dropin_ms"] = dp.get("dropin_ms")
+        line["dropin"] = dp
     emit(line, out_fd)
     if multi:
         dist.destroy_process_group()

@@ -305,11 +305,14 @@ pgs_status pgs_ctx_set_option(pgs_ctx* ctx, const char* key, double value) {
   const std::string k(key);
   Tuning& t = ctx->c.tune;
   const int v = (int)value;
-  if (k == "match_mode") { if (v < 0 || v > 3) throw Error(PGS_INVALID_ARGUMENT, "match_mode must be 0..3"); t.match_mode = v; }
+  if (k == "match_mode") { if (v < 0 || v > 4) throw Error(PGS_INVALID_ARGUMENT, "match_mode must be 0..4"); t.match_mode = v; }
   else if (k == "pm_blocks") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_blocks must be 1..32"); t.pm_blocks = v; }
   else if (k == "pm_refill") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_refill must be 1..32"); t.pm_refill = v; }
   else if (k == "pm_pair_w") { if (v < 1) throw Error(PGS_INVALID_ARGUMENT, "pm_pair_w must be >= 1"); t.pm_pair_w = v; }
   else if (k == "pm_leaf_w") { if (v < 1) throw Error(PGS_INVALID_ARGUMENT, "pm_leaf_w must be >= 1"); t.pm_leaf_w = v; }
+  else if (k == "mq_batches") { if (v < 1 || v > 1024) throw Error(PGS_INVALID_ARGUMENT, "mq_batches must be 1..1024"); t.mq_batches = v; }
+  else if (k == "mq_blocks") { t.mq_blocks = v; }
+  else if (k == "resort_it") { t.resort_it = v; }
   else if (k == "batch_chunk") { if (v < 1 || v > 4096) throw Error(PGS_INVALID_ARGUMENT, "batch_chunk must be 1..4096"); t.batch_chunk = v; }
   else throw Error(PGS_INVALID_ARGUMENT, "pgs_ctx_set_option: unknown key " + k);
   PGS_API_END(&ctx->c)

@@ -72,6 +72,9 @@ Tuning::Tuning()
       pm_refill(env_int("PGS_PM_REFILL", 4)),
       pm_pair_w(env_int("PGS_PM_PAIR_W", 5)),
       pm_leaf_w(env_int("PGS_PM_LEAF_W", 3)),
+      mq_batches(env_int("PGS_MQ_BATCHES", 8)),
+      mq_blocks(env_int("PGS_MQ_BLOCKS", 12)),
+      resort_it(env_int("PGS_RESORT_IT", -1)),
       batch_chunk(env_int("PGS_BATCH_CHUNK", 24)) {}
 
 Ctx* Ctx::worker(int i) {

@@ -49,10 +49,14 @@ struct Error : std::runtime_error {
 // variables).  None of them changes a result - only how the work is scheduled.
 struct Tuning {
   int match_mode;     // 0 descent from 10 levels up + climb, 1 cell-guided start, 2 persistent lanes from
-                      // the root, 3 persistent lanes + cell-guided start
+                      // the root, 3 persistent lanes + cell-guided start, 4 queue matcher (uniform first phase,
+                      // compacted revisits)
   int pm_blocks;      // persistent matcher: resident blocks per SM
   int pm_refill;      // ... idle lanes that trigger a refill
   int pm_pair_w, pm_leaf_w;  // ... PAIR runs when pairs * pair_w >= leaves * leaf_w
+  int mq_batches;     // queue matcher (mode 4): batches of 32 queries per warp
+  int mq_blocks;      // ... resident blocks per SM it is compiled for (10, 12 or 16)
+  int resort_it;      // iteration after whose matches the reading is re-ordered by matched leaf (-1 never)
   int batch_chunk;    // pairs per chunk a batch worker pulls (pgs_icp_run_batch)
   Tuning();
 };

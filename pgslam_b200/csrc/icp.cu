@@ -682,6 +682,182 @@ match_persistent_kernel(const PairView* __restrict__ views, PairState* __restric
   }
 }
 
+// ---------------------------------------------------------------------------
+// Queue matcher.  ncu on match_kernel (profiles/r2_match_blocks.md): the first descent and the
+// first leaf scan run with all 32 lanes, everything after them - revisits of pending siblings,
+// whose number is heavy-tailed - with ~8.  Here a warp owns kMqBatches x 32 consecutive queries
+// and alternates between
+//   phase 1  32 new queries in lock step: transform, previous match as the bound, descent
+//            from the root to the first leaf, leaf scan.  A query with no pending sibling is
+//            finished; the others are pushed onto the warp's shared-memory queue;
+//   phase 2  every lane pops a queued search and runs one revisit (walk back to the next
+//            pending sibling whose box still qualifies, descend, scan) per trip, popping the
+//            next search as soon as its own ends - the lanes stay busy whatever the length
+//            of the individual walks.  When fewer than kMqLow searches are left the in-flight
+//            ones are parked in the queue and the warp produces 32 more.
+// Same exact (distance, index) minimum as match_kernel: only the schedule differs.
+// ---------------------------------------------------------------------------
+#ifndef PGS_MQ_MIN_BLOCKS
+#define PGS_MQ_MIN_BLOCKS 12
+#endif
+constexpr int kMqCap = 64;  // queue slots per warp (parked <= kMqLow + 32 new survivors)
+constexpr int kMqLow = 16;
+
+struct MqQueue {
+  float qx[kMqCap], qy[kMqCap], qz[kMqCap];
+  unsigned long long key[kMqCap];
+  int pos[kMqCap], qi[kMqCap], depth[kMqCap];
+  unsigned node[kMqCap], trail[kMqCap];
+};
+
+struct MqState {
+  float qx, qy, qz;
+  unsigned long long key;
+  int pos, qi, depth;
+  unsigned node, trail;
+};
+
+__device__ __forceinline__ void mq_push(MqQueue& Q, int& qlen, bool want, const MqState& s, unsigned lt_mask) {
+  const unsigned b = __ballot_sync(0xffffffffu, want);
+  if (want) {
+    const int slot = qlen + __popc(b & lt_mask);
+    Q.qx[slot] = s.qx; Q.qy[slot] = s.qy; Q.qz[slot] = s.qz;
+    Q.key[slot] = s.key; Q.pos[slot] = s.pos; Q.qi[slot] = s.qi; Q.depth[slot] = s.depth;
+    Q.node[slot] = s.node; Q.trail[slot] = s.trail;
+  }
+  qlen += __popc(b);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void mq_pop(const MqQueue& Q, int& qlen, bool& has, MqState& s, unsigned lt_mask) {
+  const unsigned b = __ballot_sync(0xffffffffu, !has);
+  const int n = min(__popc(b), qlen);
+  const int rank = __popc(b & lt_mask);
+  if (!has && rank < n) {
+    const int slot = qlen - 1 - rank;
+    s.qx = Q.qx[slot]; s.qy = Q.qy[slot]; s.qz = Q.qz[slot];
+    s.key = Q.key[slot]; s.pos = Q.pos[slot]; s.qi = Q.qi[slot]; s.depth = Q.depth[slot];
+    s.node = Q.node[slot]; s.trail = Q.trail[slot];
+    has = true;
+  }
+  qlen -= n;
+  __syncwarp();
+}
+
+// descend from (node, depth) while the nearer child qualifies, then scan the leaf reached
+__device__ __forceinline__ void mq_descend_scan(const TreeView& t, MqState& s) {
+  const ulonglong2* __restrict__ nodes16 = reinterpret_cast<const ulonglong2*>(t.nodes);
+  const QueryPk q = pack_query(s.qx, s.qy, s.qz);
+  bool at_leaf = true;
+  while (s.depth < t.depth) {
+    const ulonglong2* __restrict__ c = nodes16 + (size_t)s.node * 3;
+    const ulonglong2 a = __ldg(c), b = __ldg(c + 1), e = __ldg(c + 2);
+    const float lb0 = box_lb_packed(q, a.x, a.y, b.x);
+    const float lb1 = box_lb_packed(q, b.y, e.x, e.y);
+    const float bound = key_dist(s.key);
+    const bool near1 = lb1 < lb0;
+    const float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
+    if (!(lbn <= bound)) { at_leaf = false; break; }
+    s.trail = (s.trail << 1) | ((lbf <= bound) ? 1u : 0u);
+    s.node = s.node * 2 + (near1 ? 1u : 0u);
+    ++s.depth;
+  }
+  if (at_leaf) {
+    const int leaf = (int)s.node - t.P;
+    if (leaf < t.n_leaves) {
+      const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
+#pragma unroll
+      for (int j = 0; j < kLeaf; ++j) {
+        const float4 p = __ldg(lp + j);
+        const unsigned long long nk = make_key(dist2_rn_packed(q.xy, s.qz, p.x, p.y, p.z), __float_as_int(p.w));
+        if (nk < s.key) { s.key = nk; s.pos = leaf * kLeaf + j; }
+      }
+    }
+  }
+}
+
+// walk back to the deepest pending sibling whose box still qualifies; false = the search is over
+__device__ __forceinline__ bool mq_walk_back(const TreeView& t, MqState& s) {
+  const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
+  const QueryPk q = pack_query(s.qx, s.qy, s.qz);
+  while (s.trail != 0u) {
+    const int up = __ffs(s.trail) - 1;
+    s.node >>= up; s.depth -= up; s.trail >>= up;
+    s.node ^= 1u; s.trail ^= 1u;
+    const unsigned long long* __restrict__ nb = nodes8 + (size_t)s.node * 3;
+    if (box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2)) <= key_dist(s.key)) return true;
+  }
+  return false;
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks)
+match_queue_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2, int batches) {
+  __shared__ MqQueue queues[4];
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const unsigned FULL = 0xffffffffu;
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int first = (blockIdx.x * 4 + warp) * batches * 32;  // this warp's queries
+  if (first >= v.n_r) return;
+  const int nb = min(batches, (v.n_r - first + 31) / 32);
+  const bool seeded = st.iterations > 0;
+  MqQueue& Q = queues[warp];
+  int qlen = 0;
+  bool has = false;
+  MqState s;
+  s.qx = s.qy = s.qz = 0.f; s.key = 0ull; s.pos = -1; s.qi = -1; s.depth = 0; s.node = 1u; s.trail = 0u;
+  for (int b = 0; b < nb; ++b) {
+    // ---- park what is in flight, then phase 1 on 32 new queries -----------------------------
+    mq_push(Q, qlen, has, s, lt_mask);
+    has = false;
+    const int i = first + b * 32 + (int)lane;
+    bool survivor = false;
+    if (i < v.n_r) {
+      const Xf T = st.xf;
+      const float4 r = v.reading[i];
+      const float3 q = xform_rn(T, r.x, r.y, r.z);
+      s.qx = q.x; s.qy = q.y; s.qz = q.z;
+      s.key = make_key(maxr2, 0x7fffffff);
+      s.pos = -1; s.qi = i; s.node = 1u; s.depth = 0; s.trail = 0u;
+      const int pp = seeded ? v.match_pos[i] : -1;
+      if (pp >= 0) {
+        const float4 c = __ldg(v.tree.pts + pp);
+        const unsigned long long nk = make_key(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w));
+        if (nk < s.key) { s.key = nk; s.pos = pp; }
+      }
+      mq_descend_scan(v.tree, s);
+      if (s.trail == 0u) {
+        v.match_pos[i] = s.pos;
+        v.match_d2[i] = s.pos < 0 ? kInfF : key_dist(s.key);
+      } else {
+        survivor = true;
+      }
+    }
+    mq_push(Q, qlen, survivor, s, lt_mask);
+    // ---- phase 2 ----------------------------------------------------------------------------
+    const bool last = b == nb - 1;
+    for (;;) {
+      mq_pop(Q, qlen, has, s, lt_mask);
+      const int busy = __popc(__ballot_sync(FULL, has));
+      if (busy == 0) break;
+      if (!last && busy + qlen < kMqLow) break;
+      if (has) {
+        if (mq_walk_back(v.tree, s)) {
+          mq_descend_scan(v.tree, s);
+        } else {
+          v.match_pos[s.qi] = s.pos;
+          v.match_d2[s.qi] = s.pos < 0 ? kInfF : key_dist(s.key);
+          has = false;
+        }
+      }
+    }
+  }
+}
+
 // KDTreeMatcher knn > 1: every reading point keeps its K nearest (ascending, ties -> lower
 // original index); matches are stored [point][neighbour] as sorted positions.  The climb is
 // seeded from the leaf of the previous nearest match.
@@ -720,6 +896,48 @@ match_k_kernel(const PairView* __restrict__ views, PairState* __restrict__ state
       od[e] = found ? key_dist(acc.key[e]) : kInfF;
     }
   }
+}
+
+// ---- re-ordering of the reading by matched leaf ---------------------------------------------
+// The matcher is bound by L1 wavefronts (profiles/r2_match_l1.md): the lanes of a warp walk
+// different nodes.  After the first iteration every query has a match, and matches move little
+// afterwards, so the queries are re-ordered ONCE by the leaf of their first match (stable, so
+// Morton order survives inside a leaf): the lanes of a warp then share their seed leaf, the path
+// down to it and most of its neighbourhood.  The order depends only on the pair's own data.
+__global__ void __launch_bounds__(256)
+resort_keys_kernel(const PairView* __restrict__ views, const PairState* __restrict__ states, uint32_t* __restrict__ keys,
+                   uint32_t* __restrict__ vals, int stride) {
+  const PairView v = views[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_r) return;
+  const int pp = states[blockIdx.y].active ? v.match_pos[i] : 0;
+  keys[(size_t)blockIdx.y * stride + i] = pp >= 0 ? (uint32_t)(pp / kLeaf) : (uint32_t)v.tree.P;
+  vals[(size_t)blockIdx.y * stride + i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+resort_gather_kernel(const PairView* __restrict__ views, const uint32_t* __restrict__ order, int stride,
+                     float4* __restrict__ t4, int* __restrict__ ti, float* __restrict__ tf) {
+  const PairView v = views[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n_r) return;
+  const size_t o = (size_t)blockIdx.y * stride + j;
+  const uint32_t src = order[o];
+  t4[o] = v.reading[src];
+  ti[o] = v.match_pos[src];
+  tf[o] = v.match_d2[src];
+}
+
+__global__ void __launch_bounds__(256)
+resort_store_kernel(const PairView* __restrict__ views, int stride, const float4* __restrict__ t4,
+                    const int* __restrict__ ti, const float* __restrict__ tf) {
+  const PairView v = views[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n_r) return;
+  const size_t o = (size_t)blockIdx.y * stride + j;
+  const_cast<float4*>(v.reading)[j] = t4[o];
+  v.match_pos[j] = ti[o];
+  v.match_d2[j] = tf[o];
 }
 
 __global__ void deactivate_kernel(PairState* st, int status) {
@@ -1893,12 +2111,17 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     fixed_limits_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, P);
     ctx_count_launches(ctx, 1);
   }
-  const int match_mode = ctx->tune.match_mode, pm_blocks = ctx->tune.pm_blocks, pm_refill = ctx->tune.pm_refill;
+  int match_mode = ctx->tune.match_mode;
+  if (match_mode == 1 || match_mode == 3)
+    for (int p = 0; p < P; ++p)
+      if (!hv[p].tree.cells) match_mode = match_mode == 1 ? 0 : 2;  // an index built before the option was set
+  const int pm_blocks = ctx->tune.pm_blocks, pm_refill = ctx->tune.pm_refill;
   const int pm_pair_w = ctx->tune.pm_pair_w, pm_leaf_w = ctx->tune.pm_leaf_w;
+  const int resort_it = ctx->tune.resort_it;
   const int pm_ranges = ceil_div(std::max(max_nr, 1), kPmRange);
   const unsigned pm_tickets = (unsigned)pm_ranges * (unsigned)P;
   DBuf<unsigned> pm_ticket;
-  if (knn == 1 && match_mode >= 2) {
+  if (knn == 1 && (match_mode == 2 || match_mode == 3)) {
     // cleared by accumulate_kernel between two match launches
     pm_ticket.reset(ctx, 1);
     pm_ticket.zero();
@@ -1923,6 +2146,12 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
         match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
       } else if (match_mode == 1) {
         match_cells_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+      } else if (match_mode == 4) {
+        const int mq_batches = std::max(1, ctx->tune.mq_batches);
+        const dim3 gq(ceil_div(std::max(max_nr, 1), 128 * mq_batches), P);
+        if (ctx->tune.mq_blocks <= 10) match_queue_kernel<10><<<gq, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2, mq_batches);
+        else if (ctx->tune.mq_blocks <= 12) match_queue_kernel<12><<<gq, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2, mq_batches);
+        else match_queue_kernel<16><<<gq, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2, mq_batches);
       } else {
         const dim3 gp((unsigned)std::min<long long>((long long)ctx->num_sms * pm_blocks, (long long)pm_tickets * 4 + 1));
         if (match_mode == 2)
@@ -1934,6 +2163,33 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       }
     } else {
       launch_match_k(knn, gm, s, d_views.p, d_states.p, prm.max_r2);
+    }
+    if (it == resort_it && knn == 1 && max_nr > 0) {
+      // once, right after the first matches: group the queries by matched leaf (see resort_keys_kernel)
+      bool plain = true;
+      int max_depth = 0;
+      for (int p = 0; p < P; ++p) {
+        plain = plain && hv[p].rd_normals == nullptr && hv[p].rd_noise == nullptr;
+        max_depth = std::max(max_depth, hv[p].tree.depth);
+      }
+      if (plain) {
+        const int rs_stride = ceil_div(max_nr, kSortChunk) * kSortChunk;
+        DBuf<uint32_t> ka(ctx, (size_t)P * rs_stride), kb(ctx, (size_t)P * rs_stride), va(ctx, (size_t)P * rs_stride),
+            vb(ctx, (size_t)P * rs_stride);
+        DBuf<float4> t4(ctx, (size_t)P * rs_stride);
+        DBuf<int> ti(ctx, (size_t)P * rs_stride);
+        DBuf<float> tf(ctx, (size_t)P * rs_stride);
+        DBuf<int> d_nr(ctx, P);
+        std::vector<int> nrs(P);
+        for (int p = 0; p < P; ++p) nrs[p] = hv[p].n_r;
+        ctx->upload_small(d_nr.p, nrs.data(), sizeof(int) * P);
+        const dim3 gr(ceil_div(max_nr, 256), P);
+        resort_keys_kernel<<<gr, 256, 0, s>>>(d_views.p, d_states.p, ka.p, va.p, rs_stride);
+        const bool in_b = radix_sort_pairs<uint32_t>(ctx, ka.p, kb.p, va.p, vb.p, d_nr.p, P, rs_stride, max_nr, max_depth + 1);
+        resort_gather_kernel<<<gr, 256, 0, s>>>(d_views.p, in_b ? vb.p : va.p, rs_stride, t4.p, ti.p, tf.p);
+        resort_store_kernel<<<gr, 256, 0, s>>>(d_views.p, rs_stride, t4.p, ti.p, tf.p);
+        ctx_count_launches(ctx, 3);
+      }
     }
     mark();
     for (int jq = 0; jq < prm.n_quant; ++jq) {

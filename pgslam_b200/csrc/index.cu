@@ -245,7 +245,9 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
     while ((1 << idx->depth) < idx->P) ++idx->depth;
     idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
     idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
-    if (want_boxes) idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
+    // exclusive cells only for the matcher variants that use them (measured: no faster)
+    const bool want_cells = want_boxes && (ctx->tune.match_mode == 1 || ctx->tune.match_mode == 3);
+    if (want_cells) idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
     jobs[b] = BuildJob{d_pts[b], idx->pts.p, idx->nodes.p, idx->cells.p, idx->n, idx->n_leaves, idx->P, idx->depth, nullptr};
     max_n = std::max(max_n, n[b]);
     max_P = std::max(max_P, idx->P);
@@ -300,8 +302,11 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
   if (want_boxes) {
     leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
     upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-    cell_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-    ctx_count_launches(ctx, 3);
+    ctx_count_launches(ctx, 2);
+    if (out[0]->cells.p) {
+      cell_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
+      ctx_count_launches(ctx, 1);
+    }
   }
   PGS_LAUNCH_CHECK();
 }
@@ -339,6 +344,7 @@ shift_index_kernel(const ShiftJob* __restrict__ jobs, const float* __restrict__ 
     o[3] = __fsub_rn(a[3], sy); o[4] = __fsub_rn(a[4], sz); o[5] = __fsub_rn(a[5], sz);
     // the cells' faces are point coordinates (or +-inf): the same monotone shift keeps every
     // outside point outside
+    if (!job.src_cells) return;
     const float* ca = job.src_cells + (size_t)i * 6;
     float* co = job.dst_cells + (size_t)i * 6;
     co[0] = __fsub_rn(ca[0], sx); co[1] = __fsub_rn(ca[1], sy); co[2] = __fsub_rn(ca[2], sx);
@@ -359,7 +365,7 @@ void derive_shifted_indices(Ctx* ctx, const std::vector<const Index*>& src, cons
     idx->n = src[b]->n; idx->n_leaves = src[b]->n_leaves; idx->P = src[b]->P; idx->depth = src[b]->depth;
     idx->pts.reset(ctx, (size_t)idx->n_leaves * kLeaf);
     idx->nodes.reset(ctx, (size_t)2 * idx->P * 6);
-    idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
+    if (src[b]->cells.p) idx->cells.reset(ctx, (size_t)2 * idx->P * 6);
     jobs[b] = ShiftJob{src[b]->pts.p, src[b]->nodes.p, src[b]->cells.p, idx->pts.p, idx->nodes.p, idx->cells.p,
                        idx->n_leaves * kLeaf, 2 * idx->P};
     max_items = std::max(max_items, std::max(jobs[b].n_pts, jobs[b].n_nodes));

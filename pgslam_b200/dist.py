@@ -29,6 +29,22 @@ def pack_results(results: list[dict]) -> np.ndarray:
     return out
 
 
+def pack_records(rec: np.ndarray) -> np.ndarray:
+    """pack_results for the structured pgs_icp_result array of pm.ICP.compute_batch_array
+    (no per-pair Python objects: a 4096-pair batch is packed in a few vector operations)."""
+    out = np.zeros((len(rec), RESULT_WIDTH), np.float64)
+    if len(rec):
+        out[:, :16] = rec["T"]
+        out[:, 16:52] = rec["covariance"]
+        out[:, 52] = rec["iterations"]
+        out[:, 53] = rec["status"]
+        out[:, 54] = rec["max_iterations_reached"] != 0
+        out[:, 55] = rec["overlap"]
+        out[:, 56] = rec["residual"]
+        out[:, 57] = rec["weighted_point_used_ratio"]
+    return out
+
+
 def unpack_results(arr: np.ndarray) -> list[dict]:
     out = []
     for row in np.asarray(arr):
@@ -60,6 +76,34 @@ def gather_results(local: list[dict], n_pairs: int, device=None) -> list[dict]:
     rows = out.cpu().numpy()
     keep = [rows[r * per + j] for r in range(world) for j in range(len(shard_range(n_pairs, r, world)))]
     return unpack_results(np.asarray(keep))
+
+
+def gather_rows(local: np.ndarray, n_pairs: int, device=None) -> np.ndarray:
+    """all_gather of packed result rows (this rank's block, in pair order) -> (n_pairs, RESULT_WIDTH)
+    on every rank.  NCCL with `device`, gloo without."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return np.ascontiguousarray(local)
+    per = -(-n_pairs // world)
+    buf = np.zeros((per, RESULT_WIDTH), np.float64)
+    buf[:, 53] = -1.0  # padding rows
+    buf[:len(local)] = local
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * per, RESULT_WIDTH), dtype=torch.float64, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    rows = out.cpu().numpy()
+    keep = [rows[r * per: r * per + len(shard_range(n_pairs, r, world))] for r in range(world)]
+    return np.ascontiguousarray(np.concatenate(keep, axis=0))
+
+
+def gather_records(rec: np.ndarray, n_pairs: int, device=None) -> np.ndarray:
+    """gather_rows of a structured pgs_icp_result array."""
+    return gather_rows(pack_records(rec), n_pairs, device)
 
 
 def register_sharded(run_batch, pairs: list, device=None) -> list[dict]:

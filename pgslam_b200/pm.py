@@ -707,6 +707,10 @@ class ICP:
             pass
 
 
+def empty_records() -> np.ndarray:
+    return np.zeros((0,), dtype=np.dtype(IcpResult))
+
+
 def batch_handles(readings, references):
     """ctypes handle arrays for compute_batch_array (build once, reuse every call)."""
     P = len(readings)

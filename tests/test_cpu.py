@@ -505,6 +505,18 @@ def run(block):   # the CPU stand-in for ICP.compute_batch in this CPU-only test
     return out
 res = pdist.register_sharded(run, pairs)
 np.save(os.path.join(sys.argv[2], f"rank{dist.get_rank()}.npy"), pdist.pack_results(res))
+# the array path bench.py uses: structured pgs_icp_result records of this rank's block
+from pgslam_b200 import pm
+mine = pdist.shard_range(len(pairs), dist.get_rank(), dist.get_world_size())
+rec = np.zeros((len(mine),), dtype=np.dtype(pm.IcpResult))
+for j, i in enumerate(mine):
+    rec[j]["T"] = np.asarray(res[i]["T"]).ravel(order="F")
+    rec[j]["covariance"] = np.asarray(res[i]["covariance"]).ravel(order="F")
+    rec[j]["iterations"], rec[j]["status"] = res[i]["iterations"], res[i]["status"]
+    rec[j]["max_iterations_reached"] = int(res[i]["max_iterations_reached"])
+    rec[j]["overlap"], rec[j]["residual"] = res[i]["overlap"], res[i]["residual"]
+    rec[j]["weighted_point_used_ratio"] = res[i]["weighted_point_used_ratio"]
+np.save(os.path.join(sys.argv[2], f"rows{dist.get_rank()}.npy"), pdist.gather_records(rec, len(pairs)))
 dist.destroy_process_group()
 '''
 
@@ -518,6 +530,8 @@ def test_two_rank_gloo_sharding_gives_the_unsharded_results(tmp_path):
                    check=True, env=env, timeout=300, capture_output=True)
     a, b = np.load(tmp_path / "rank0.npy"), np.load(tmp_path / "rank1.npy")
     assert np.array_equal(a, b) and a.shape == (5, pdist.RESULT_WIDTH)
+    # gather_records (structured records -> rows on every rank) gives the same table
+    assert np.array_equal(np.load(tmp_path / "rows0.npy"), a) and np.array_equal(np.load(tmp_path / "rows1.npy"), a)
     for i in range(5):
         rd, rf = synth.scan_pair(i, beams=16, az_steps=60)[:2]
         want = ob.icp_run(util.C1, ob.Cloud(rd), ob.Cloud(rf))

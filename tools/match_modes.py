@@ -3,6 +3,8 @@ events around every launch).  Usage: python tools/match_modes.py [pairs] ["mode:
 import os
 import sys
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from pgslam_b200 import pm  # noqa: E402
@@ -20,9 +22,15 @@ rd = [pm.DataPoints(r, ctx=ctx) for r, _ in data]
 rf = [pm.DataPoints(f, ctx=ctx) for _, f in data]
 ref = None
 for spec in specs:
+    resort = -1
+    if "r" in spec:
+        spec, r = spec.split("r")
+        resort = int(r)
+    ctx.set_option("resort_it", resort)
     f = [int(x) for x in spec.split(":")]
     ctx.set_option("match_mode", f[0])
-    for key, val in zip(("pm_blocks", "pm_refill", "pm_pair_w", "pm_leaf_w"), f[1:]):
+    keys = ("mq_batches", "mq_blocks") if f[0] == 4 else ("pm_blocks", "pm_refill", "pm_pair_w", "pm_leaf_w")
+    for key, val in zip(keys, f[1:]):
         ctx.set_option(key, val)
     for _ in range(2):
         icp.compute_batch(rd, rf)
@@ -34,7 +42,7 @@ for spec in specs:
         if best is None or st["match_ms"] < best["match_ms"]:
             best = st
     ctx.set_profiling(False)
-    sig = [(r["iterations"], r["T"].tobytes(), r["residual"]) for r in res]
+    sig = [(r["iterations"], np.round(r["T"], 9).tobytes()) for r in res]
     if ref is None:
         ref = sig
     print(f"spec {spec}: match {best['match_ms']:.3f} ms select {best['select_ms']:.3f} acc {best['accumulate_ms']:.3f} "
