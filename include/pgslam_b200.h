@@ -243,6 +243,19 @@ pgs_status pgs_config_check(const char *yaml, size_t len, int is_chain,
  * name of the i-th one.                                                       */
 int pgs_registrar_count(int kind);
 const char *pgs_registrar_name(int kind, int index);
+/* Parametrizable::availableParameters(): number of documented parameters of a
+ * registered module (-1: unknown module) and the i-th one; every returned
+ * string is static ("" = unbounded).  Types: 'i' integer, 'u' bool/unsigned,
+ * 'f' real, 's' string.                                                       */
+int pgs_registrar_param_count(int kind, const char *name);
+pgs_status pgs_registrar_param(int kind, const char *name, int index, const char **key,
+                               const char **doc, const char **default_value,
+                               const char **min_value, const char **max_value, char *type);
+/* REG(kind).create(name, params) without a device: validates the name and the
+ * parameters exactly as the creators above do (TransformationChecker,
+ * Inspector, Logger and Transformation modules have no device object).       */
+pgs_status pgs_module_validate(int kind, const char *name, const char *const *kv, int nkv,
+                               char *err, int cap);
 
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context launched since creation (bench.py's

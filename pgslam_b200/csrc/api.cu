@@ -286,6 +286,48 @@ const char* pgs_registrar_name(int kind, int index) {
   return name.c_str();
 }
 
+int pgs_registrar_param_count(int kind, const char* name) {
+  if (kind < 0 || kind > 7 || !name) return -1;
+  const std::vector<ParamDoc>* p = module_params((Kind)kind, name);
+  return p ? (int)p->size() : -1;
+}
+
+pgs_status pgs_registrar_param(int kind, const char* name, int index, const char** key, const char** doc,
+                               const char** default_value, const char** min_value, const char** max_value, char* type) {
+  if (kind < 0 || kind > 7 || !name) return PGS_INVALID_ARGUMENT;
+  const std::vector<ParamDoc>* p = module_params((Kind)kind, name);
+  if (!p) return PGS_INVALID_ELEMENT;
+  if (index < 0 || index >= (int)p->size()) return PGS_INVALID_ARGUMENT;
+  const ParamDoc& d = (*p)[index];
+  if (key) *key = d.name;
+  if (doc) *doc = d.doc;
+  if (default_value) *default_value = d.def;
+  if (min_value) *min_value = d.min;
+  if (max_value) *max_value = d.max;
+  if (type) *type = d.type;
+  return PGS_OK;
+}
+
+pgs_status pgs_module_validate(int kind, const char* name, const char* const* kv, int nkv, char* err, int cap) {
+  int code = PGS_OK;
+  std::string msg;
+  try {
+    if (kind < 0 || kind > 7 || !name) throw Error(PGS_INVALID_ARGUMENT, "pgs_module_validate: bad arguments");
+    create_module((Kind)kind, name, kv_params(kv, nkv));
+  } catch (const pgs::Error& ex) {
+    code = ex.code;
+    msg = ex.what();
+  } catch (const std::exception& ex) {
+    code = PGS_INVALID_ARGUMENT;
+    msg = ex.what();
+  }
+  if (err && cap > 0) {
+    std::strncpy(err, msg.c_str(), cap - 1);
+    err[cap - 1] = '\0';
+  }
+  return (pgs_status)code;
+}
+
 uint64_t pgs_ctx_launch_count(const pgs_ctx* ctx) { return ctx->c.launches; }
 
 pgs_status pgs_ctx_set_profiling(pgs_ctx* ctx, int enabled) {

@@ -134,6 +134,9 @@ SIGNATURES = {
     "pgs_config_check": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "pgs_registrar_count": (C.c_int, [C.c_int]),
     "pgs_registrar_name": (C.c_char_p, [C.c_int, C.c_int]),
+    "pgs_registrar_param_count": (C.c_int, [C.c_int, C.c_char_p]),
+    "pgs_registrar_param": (C.c_int, [C.c_int, C.c_char_p, C.c_int] + [C.POINTER(C.c_char_p)] * 5 + [C.c_char_p]),
+    "pgs_module_validate": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
     "pgs_ctx_launch_count": (C.c_uint64, [_vp]),
     "pgs_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "pgs_ctx_set_batch_streams": (C.c_int, [_vp, C.c_int]),
@@ -181,6 +184,23 @@ def registered(kind: str) -> list[str]:
     L = load_library()
     k = KINDS.index(kind)
     return [L.pgs_registrar_name(k, i).decode() for i in range(L.pgs_registrar_count(k))]
+
+
+def available_parameters(kind: str, name: str) -> list[dict]:
+    """Parametrizable::availableParameters() of a registered module."""
+    L = load_library()
+    k = KINDS.index(kind)
+    n = L.pgs_registrar_param_count(k, name.encode())
+    if n < 0:
+        raise InvalidElement(INVALID_ELEMENT, f"Trying to instanciate unknown element {name}")
+    out = []
+    for i in range(n):
+        f = [C.c_char_p() for _ in range(5)]
+        t = C.create_string_buffer(2)
+        L.pgs_registrar_param(k, name.encode(), i, *[C.byref(x) for x in f], t)
+        out.append(dict(name=f[0].value.decode(), doc=f[1].value.decode(), default=f[2].value.decode(),
+                        min=f[3].value.decode(), max=f[4].value.decode(), type=t.value.decode()))
+    return out
 
 
 def _mat(T):

@@ -13,13 +13,21 @@ from tests import util
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def build_callsites(out_dir=None):
+    """compile tests/cpp/callsites.cpp against the adapter (also used by bench.py's drop-in leg)"""
+    import pathlib
+    import tempfile
+    d = pathlib.Path(out_dir or tempfile.mkdtemp(prefix="pgs_callsites_"))
+    return _compile(d)
+
+
 def _compile(tmp_path):
     build.build()
     exe = str(tmp_path / "callsites")
     libdir = os.path.dirname(pm.LIB_PATH)
     subprocess.run(["/usr/bin/g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "cpp", "callsites.cpp"), "-o", exe, "-L" + libdir, "-lpgslam_b200",
-                    "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+                    "-Wl,-rpath," + libdir, "-pthread"], check=True, capture_output=True, text=True)
     return exe
 
 
@@ -67,3 +75,31 @@ def test_pgslam_call_sites_run_and_match_the_oracle(tmp_path):
     assert st == 0 and float(kv["weighted_ratio"]) == pytest.approx(ratio, abs=1e-6)
     assert int(kv["local_map_points"]) == rd.shape[1] + rf.shape[1]
     assert int(kv["has_map_before"]) == 0 and int(kv["seq_iterations"]) >= 1
+    assert int(kv["no_map_identity"]) == 1
+    # plugin registrar, YAML-free
+    assert kv["reg_filter_class"] == "RandomSamplingDataPointsFilter" and kv["reg_filter_seed_default"] == "0"
+    assert int(kv["reg_filter_nparams"]) == 2 and 0.4 * rf.shape[1] < int(kv["reg_filter_points"]) < 0.6 * rf.shape[1]
+    ids, _ = ob.kdtree_knn(rf, rd, k=2)
+    assert int(kv["reg_matcher_k"]) == 2 and int(kv["reg_matcher_id0"]) == int(ids[0, 0])
+    assert float(kv["reg_outlier_ratio"]) == pytest.approx(0.5, abs=1e-3) and int(kv["reg_outlier_chain_equal"]) == 1
+    assert np.isfinite(float(kv["reg_minimizer_t03"])) and int(kv["reg_checker_max"]) == 7
+    assert int(kv["reg_errors"]) == 7 and int(kv["reg_names"]) >= 15
+    # times follow the points through a device filter
+    assert int(kv["times_cols"]) == int(kv["times_points"]) > 0 and int(kv["times_bad"]) == 0
+    # the candidate loop as one batch: same answers as the single calls, on one or two contexts
+    Tb = np.array([float(x) for x in kv["T_batch0"].split(",")]).reshape(4, 4).T
+    assert np.array_equal(Tb, T) and int(kv["batch_iterations0"]) == want["iterations"]
+    assert int(kv["batch_converged"]) == 1 and int(kv["batch_two_contexts_equal"]) == 1
+    assert int(kv["batch_pair2_status"]) == ob.icp_run(cfg, orf, orf)["status"]
+    # T = double: the pose is returned in double, not through float
+    Td = np.array([float(x) for x in kv["T_double"].split(",")]).reshape(4, 4).T
+    assert np.abs(Td - want["T"]).max() < 1e-9 and not np.array_equal(Td, Td.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.gpu
+def test_dropin_bench_mode(tmp_path):
+    import json
+    exe = _compile(tmp_path)
+    out = subprocess.run([exe, "--bench", "20000"], check=True, capture_output=True, text=True, timeout=120).stdout
+    d = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][0])
+    assert d["points"] == 20000 and d["dropin_ms"] > 0 and d["dropin_ms_unchanged_clouds"] <= d["dropin_ms"] * 1.5
