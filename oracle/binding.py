@@ -105,6 +105,9 @@ def lib():
     L.orc_kdtree_free.argtypes = [C.c_void_p]
     L.orc_kdtree_knn.restype = C.c_uint64
     L.orc_kdtree_knn.argtypes = [C.c_void_p, _fp, C.c_int64, C.c_int, C.c_float, C.c_int, _ip, _fp]
+    L.orc_kdtree_knn_ex.restype = C.c_uint64
+    L.orc_kdtree_knn_ex.argtypes = [C.c_void_p, _fp, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, _ip, _fp]
+    L.orc_set_search_mode.argtypes = [C.c_int]
     L.orc_knn_brute.argtypes = [_fp, C.c_int64, _fp, C.c_int64, C.c_int, C.c_float, _ip, _fp]
     L.orc_filter_apply.argtypes = [C.POINTER(CFilter), cp]
     L.orc_filters_apply.argtypes = [C.POINTER(CFilter), C.c_int, cp]
@@ -229,14 +232,24 @@ def _pts(a):
     return np.ascontiguousarray(a.T)
 
 
-def kdtree_knn(ref, query, k=1, max_dist=np.inf, allow_self=True, return_visits=False):
+SEARCH_CONTRACT, SEARCH_NABO = 0, 1
+
+
+def set_search_mode(mode: int):
+    """matcher semantics inside icp_run / icp_seq / the probes: SEARCH_CONTRACT (default) or
+    SEARCH_NABO (libnabo verbatim: strict <, first-visited ties, incremental rd, epsilon honoured)"""
+    lib().orc_set_search_mode(int(mode))
+
+
+def kdtree_knn(ref, query, k=1, max_dist=np.inf, allow_self=True, return_visits=False, mode=SEARCH_CONTRACT,
+               epsilon=0.0):
     L = lib()
     r, q = _pts(ref), _pts(query)
     nq = q.shape[0]
     ids = np.empty((nq, k), np.int32)
     d2 = np.empty((nq, k), np.float32)
     t = L.orc_kdtree_build(_f(r), r.shape[0])
-    v = L.orc_kdtree_knn(t, _f(q), nq, k, float(max_dist), int(allow_self), _i(ids), _f(d2))
+    v = L.orc_kdtree_knn_ex(t, _f(q), nq, k, float(max_dist), int(allow_self), float(epsilon), int(mode), _i(ids), _f(d2))
     L.orc_kdtree_free(t)
     return (ids.T, d2.T, v) if return_visits else (ids.T, d2.T)
 

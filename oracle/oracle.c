@@ -395,10 +395,61 @@ static void kd_recurse(kd_search *s, int64_t n) {
   s->off[cd] = old;
 }
 
-uint64_t orc_kdtree_knn(const orc_kdtree *t, const float *query4, int64_t nq, int k,
-                        float max_dist, int allow_self, int32_t *ids, float *d2) {
+/* ---- libnabo-faithful search (A.2 verbatim) -------------------------------
+ * What the contract mode above changes on purpose, undone here so that the
+ * two can be compared (tests/test_cpu.py, oracle/README.md):
+ *   - candidates enter on a STRICT distance compare (dist < headValue), and an
+ *     equal value stays behind the earlier-visited one (no index tie-break);
+ *   - the far side's lower bound is the INCREMENTAL rd += -old*old + new*new;
+ *   - pruning uses rd * (1+eps)^2 < headValue, i.e. epsilon is honoured.      */
+static inline void heap_insert_nabo(kd_heap *h, int32_t id, float d) {
+  int j = h->k - 1;
+  while (j > 0 && h->d[j - 1] > d) {
+    h->d[j] = h->d[j - 1];
+    h->id[j] = h->id[j - 1];
+    --j;
+  }
+  h->d[j] = d;
+  h->id[j] = id;
+}
+
+static void kd_recurse_nabo(kd_search *s, int64_t n, float rd, float max_error2) {
+  const kd_node *nd = &s->t->nodes[n];
+  if (nd->dim == 3) {
+    const int32_t *b = s->t->bucket + nd->right_or_start;
+    for (uint32_t i = 0; i < nd->size; ++i) {
+      int32_t pi = b[i];
+      float d = dist2_f32(s->q, s->t->pts + 4 * (int64_t)pi);
+      if (d <= s->maxr2 && d < s->h.d[s->h.k - 1] && (s->allow_self || d > FLT_EPSILON))
+        heap_insert_nabo(&s->h, pi, d);
+    }
+    s->visits++;
+    return;
+  }
+  int cd = (int)nd->dim;
+  float old = s->off[cd];
+  float nw = s->q[cd] - nd->cut;
+  int64_t nearc, farc;
+  if (nw > 0) { nearc = nd->right_or_start; farc = n + 1; }
+  else        { nearc = n + 1; farc = nd->right_or_start; }
+  kd_recurse_nabo(s, nearc, rd, max_error2);
+  rd += -old * old + nw * nw;
+  if (rd <= s->maxr2 && rd * max_error2 < s->h.d[s->h.k - 1]) {
+    s->off[cd] = nw;
+    kd_recurse_nabo(s, farc, rd, max_error2);
+    s->off[cd] = old;
+  }
+}
+
+static int g_search_mode = ORC_SEARCH_CONTRACT;
+void orc_set_search_mode(int mode) { g_search_mode = mode; }
+int orc_search_mode(void) { return g_search_mode; }
+
+uint64_t orc_kdtree_knn_ex(const orc_kdtree *t, const float *query4, int64_t nq, int k, float max_dist,
+                           int allow_self, float epsilon, int mode, int32_t *ids, float *d2) {
   uint64_t total = 0;
   float maxr2 = isinf(max_dist) ? INFINITY : max_dist * max_dist;
+  const float max_error2 = (1.f + epsilon) * (1.f + epsilon);
 #pragma omp parallel reduction(+ : total)
   {
     kd_search s;
@@ -414,11 +465,20 @@ uint64_t orc_kdtree_knn(const orc_kdtree *t, const float *query4, int64_t nq, in
       s.h.id = ids + (size_t)i * k;
       for (int j = 0; j < k; ++j) { s.h.d[j] = INFINITY; s.h.id[j] = -1; }
       s.visits = 0;
-      if (t->n > 0) kd_recurse(&s, 0);
+      if (t->n > 0) {
+        if (mode == ORC_SEARCH_NABO) kd_recurse_nabo(&s, 0, 0.f, max_error2);
+        else kd_recurse(&s, 0);
+      }
       total += s.visits;
     }
   }
   return total;
+}
+
+/* the contract: exact (eps = 0), ties -> lower index */
+uint64_t orc_kdtree_knn(const orc_kdtree *t, const float *query4, int64_t nq, int k,
+                        float max_dist, int allow_self, int32_t *ids, float *d2) {
+  return orc_kdtree_knn_ex(t, query4, nq, k, max_dist, allow_self, 0.f, ORC_SEARCH_CONTRACT, ids, d2);
 }
 
 void orc_knn_brute(const float *ref4, int64_t n, const float *query4, int64_t nq,
@@ -1909,7 +1969,8 @@ static int icp_loop(const orc_icp_config *cfg, const orc_cloud *readingIn,
     st = orc_rigid_transform(step, T_iter);
     if (st) break;
     double tk = now_s();
-    res->visits += orc_kdtree_knn(tree, step->feat, step->n, k, (float)cfg->max_dist, 1, ids, d2);
+    res->visits += orc_kdtree_knn_ex(tree, step->feat, step->n, k, (float)cfg->max_dist, 1, (float)cfg->epsilon,
+                                      g_search_mode, ids, d2);
     res->time_knn_s += now_s() - tk;
     st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, step, reference, ids, d2, k, w);
     if (st) break;
@@ -2016,7 +2077,7 @@ int orc_probe_overlap(const orc_icp_config *cfg, const orc_cloud *readingIn,
     int32_t *ids = (int32_t *)malloc((size_t)(rd->n + 1) * k * sizeof(int32_t));
     float *d2 = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     float *w = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
-    orc_kdtree_knn(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, ids, d2);
+    orc_kdtree_knn_ex(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, (float)cfg->epsilon, g_search_mode, ids, d2);
     st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, rd, ref, ids, d2, k, w);
     if (!st) {
       int64_t kept = 0;
@@ -2045,7 +2106,7 @@ int orc_probe_residual(const orc_icp_config *cfg, const orc_cloud *readingIn,
     int32_t *ids = (int32_t *)malloc((size_t)(rd->n + 1) * k * sizeof(int32_t));
     float *d2 = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
     float *w = (float *)malloc((size_t)(rd->n + 1) * k * sizeof(float));
-    orc_kdtree_knn(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, ids, d2);
+    orc_kdtree_knn_ex(t, rd->feat, rd->n, k, (float)cfg->max_dist, 1, (float)cfg->epsilon, g_search_mode, ids, d2);
     st = orc_outlier_weights_full(cfg->outliers, cfg->n_outliers, rd, reference, ids, d2, k, w);
     if (!st) {
       orc_min_out mo;

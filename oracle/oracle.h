@@ -72,6 +72,17 @@ uint64_t orc_kdtree_knn(const orc_kdtree *t, const float *query4, int64_t nq,
                         int k, float max_dist, int allow_self, int32_t *ids,
                         float *d2);
 /* O(N*M) twin: exact fp32 argmin, ties -> lower index.                     */
+/* Search semantics.  CONTRACT (default): exact, ties -> lower index, far-side bound recomputed
+ * (what the CUDA path implements; epsilon is ignored = 0).  NABO: libnabo's own rules, verbatim
+ * from SURVEY.md Appendix A.2 - strict '<', first-visited ties, incremental rd, (1+eps)^2
+ * pruning - used ONLY to measure how far the contract is from the real library
+ * (oracle/README.md).  The mode set here applies to the matcher inside orc_icp_run /
+ * orc_icp_seq_run / the probes (with the chain's `epsilon`); filters keep the contract.    */
+enum { ORC_SEARCH_CONTRACT = 0, ORC_SEARCH_NABO = 1 };
+void orc_set_search_mode(int mode);
+int orc_search_mode(void);
+uint64_t orc_kdtree_knn_ex(const orc_kdtree *t, const float *query4, int64_t nq, int k, float max_dist,
+                           int allow_self, float epsilon, int mode, int32_t *ids, float *d2);
 void orc_knn_brute(const float *ref4, int64_t n, const float *query4,
                    int64_t nq, int k, float max_dist, int32_t *ids, float *d2);
 

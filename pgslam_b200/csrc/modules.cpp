@@ -5,6 +5,7 @@
 #include "modules.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <sstream>
@@ -47,7 +48,7 @@ const std::vector<ModuleDoc>& registry() {
       {Kind::DataPointsFilter, "SurfaceNormalDataPointsFilter",
        {{"knn", "neighbours used per point", "5", "3", IMAX, 'i'},
         {"maxDist", "maximum neighbour distance", INF, "0", INF, 'f'},
-        {"epsilon", "approximation of the search (treated as 0: exact)", "0", "0", INF, 'f'},
+        {"epsilon", "approximation of the search: must be 0 (exact); see PGS_EPSILON_POLICY", "0", "0", INF, 'f'},
         {"keepNormals", "", "1", "0", "1", 'u'},
         {"keepDensities", "", "0", "0", "1", 'u'},
         {"keepEigenValues", "", "0", "0", "1", 'u'},
@@ -91,7 +92,7 @@ const std::vector<ModuleDoc>& registry() {
       // ---- Matcher (A8, A9) ----------------------------------------------
       {Kind::Matcher, "KDTreeMatcher",
        {{"knn", "number of nearest neighbours", "1", "1", IMAX, 'i'},
-        {"epsilon", "approximation (treated as 0: exact search)", "0", "0", INF, 'f'},
+        {"epsilon", "approximation of the search: must be 0 (exact); see PGS_EPSILON_POLICY", "0", "0", INF, 'f'},
         {"searchType", "libnabo search type (ignored: one exact GPU index)", "1", "0", "2", 'i'},
         {"maxDist", "maximum distance to consider", INF, "0", INF, 'f'}}},
       // ---- OutlierFilters (A10, A.3) -------------------------------------
@@ -213,6 +214,22 @@ Module create_module(Kind kind, const std::string& name, const Params& params) {
                                                " is larger than maximum admissible value " + doc->max);
     }
     m.params[kv.first] = kv.second;
+  }
+  // `epsilon` != 0 asks libnabo for an APPROXIMATE search whose answer depends on libnabo's own
+  // tree shape and visit order (oracle/README.md: 8-49 % of the ids change, poses move by
+  // centimetres).  This library searches exactly; silently doing so would return results the
+  // configuration did not ask for, so the parameter is refused unless the caller opts in.
+  auto eps = m.params.find("epsilon");
+  if (eps != m.params.end() && (name == "KDTreeMatcher" || name == "SurfaceNormalDataPointsFilter")) {
+    double v = 0;
+    if (parse_number(eps->second, &v) && v != 0.0) {
+      const char* pol = std::getenv("PGS_EPSILON_POLICY");
+      if (!(pol && std::string(pol) == "exact"))
+        throw Error(PGS_INVALID_PARAMETER, "Parameter epsilon = " + eps->second + " of " + name +
+                                               ": approximate (eps > 0) nearest-neighbour search is not implemented - this "
+                                               "library searches exactly.  Set epsilon: 0, or export PGS_EPSILON_POLICY=exact "
+                                               "to accept the exact search in its place");
+    }
   }
   return m;
 }

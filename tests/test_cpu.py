@@ -657,3 +657,64 @@ def test_bench_reference_arm_prints_one_contract_line():
         ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                               timeout=600)
         assert ours.returncode != 0 and "no CUDA device" in (ours.stderr + ours.stdout)
+
+
+# ------------------------------------------- libnabo-faithful mode vs the contract ---
+def test_libnabo_faithful_search_equals_the_contract_at_eps_0_and_not_above():
+    """oracle/README.md's divergence table, re-measured: with eps = 0 libnabo's own rules (strict <,
+    first-visited ties, incremental rd) return the same ids and distances as the contract's exact
+    (distance, index) minimum on scan data; they differ only on exact ties.  With eps > 0 libnabo is
+    approximate and a large share of the ids differ - which is why the product refuses eps != 0."""
+    rd, rf, _ = synth.scan_pair(3, beams=16, az_steps=900)
+    for k in (1, 10):
+        a = ob.kdtree_knn(rf, rd, k=k)
+        b = ob.kdtree_knn(rf, rd, k=k, mode=ob.SEARCH_NABO)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        c = ob.kdtree_knn(rf, rd, k=k, mode=ob.SEARCH_NABO, epsilon=1.0)
+        assert (a[0] != c[0]).mean() > 0.05            # approximate search: not the same neighbours
+        assert np.all(c[1][0] <= a[1][0] * 4.0 + 1e-12)  # but within (1+eps)^2 of the true nearest distance
+    # exact ties (every point three times): same distances, ids may differ (first visited vs lowest index)
+    g = np.random.default_rng(0)
+    base = g.uniform(-5, 5, size=(3, 400)).astype(np.float32)
+    ref = np.ones((4, 1200), np.float32)
+    ref[:3] = np.concatenate([base, base, base], axis=1)
+    q = np.ones((4, 200), np.float32)
+    q[:3] = g.uniform(-5, 5, size=(3, 200)).astype(np.float32)
+    a = ob.kdtree_knn(ref, q, k=3)
+    b = ob.kdtree_knn(ref, q, k=3, mode=ob.SEARCH_NABO)
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(np.sort(a[0] % 400, axis=0), np.sort(b[0] % 400, axis=0))  # the same points, other copies
+    assert np.all(a[0][0] < 400)  # the contract: lowest index of every tie
+
+
+def test_libnabo_faithful_icp_matches_the_contract_at_eps_0():
+    rd, rf, _ = synth.scan_pair(4, beams=16, az_steps=600)
+    want = ob.icp_run(util.C2, ob.Cloud(rd), ob.Cloud(rf))
+    try:
+        ob.set_search_mode(ob.SEARCH_NABO)
+        same = ob.icp_run(util.C2, ob.Cloud(rd), ob.Cloud(rf))
+        approx = ob.icp_run(dict(util.C2, matcher={"KDTreeMatcher": {"knn": 1, "epsilon": 3.16}}), ob.Cloud(rd), ob.Cloud(rf))
+    finally:
+        ob.set_search_mode(ob.SEARCH_CONTRACT)
+    assert same["iterations"] == want["iterations"] and np.array_equal(same["T"], want["T"])
+    assert np.abs(approx["T"] - want["T"]).max() > 1e-5  # eps > 0 moves the pose well beyond the 1e-5 contract
+
+
+def test_epsilon_is_rejected_not_ignored():
+    """KDTreeMatcher / SurfaceNormalDataPointsFilter `epsilon` != 0 asks for libnabo's approximate
+    search, whose result depends on libnabo's tree and visit order: refused (PGS_EPSILON_POLICY=exact
+    accepts it and runs the exact search instead)."""
+    cfg = dict(util.C2, matcher={"KDTreeMatcher": {"knn": 1, "epsilon": 3.16}})
+    with pytest.raises(pm.InvalidParameter, match="epsilon"):
+        pm.check_config(util.to_yaml(cfg))
+    cfg = dict(util.C2, referenceDataPointsFilters=[{"SurfaceNormalDataPointsFilter": {"knn": 10, "epsilon": 1.33}}])
+    with pytest.raises(pm.InvalidParameter, match="epsilon"):
+        pm.check_config(util.to_yaml(cfg))
+    with pytest.raises(pm.InvalidParameter, match="epsilon"):
+        pm.check_config(util.to_yaml([{"SurfaceNormalDataPointsFilter": {"epsilon": 0.5}}]), chain=False)
+    assert pm.check_config(util.to_yaml(util.C2)) > 0  # epsilon: 0 passes
+    env = dict(os.environ, PGS_EPSILON_POLICY="exact")
+    code = ("import sys; sys.path.insert(0, %r); from pgslam_b200 import pm; from tests import util; "
+            "print(pm.check_config(util.to_yaml(dict(util.C2, matcher={'KDTreeMatcher': {'knn': 1, 'epsilon': 3.16}}))))" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    assert int(out.strip()) > 0
