@@ -1341,7 +1341,13 @@ int orc_dists_quantile(const float *d2, int64_t nk, double q, float *out) {
   if (q < 0.0 || q > 1.0) { free(vals); return ORC_CONVERGENCE_ERROR; }
   qsort(vals, (size_t)m, sizeof(float), cmp_f32); /* exact order statistic  */
   if (q == 1.0) *out = vals[m - 1];
-  else *out = vals[(size_t)((double)m * q)];
+  else {
+    /* upstream: values.size() * quantile with quantile of type T = float (Matches.cpp), so the
+     * product is a float; (float)0.85 > 0.85, which can move the truncated rank by one */
+    size_t j = (size_t)((float)m * (float)q);
+    if (j >= (size_t)m) j = (size_t)m - 1;
+    *out = vals[j];
+  }
   free(vals);
   return ORC_OK;
 }

@@ -1028,7 +1028,8 @@ select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ s
       for (int l = 0; l < 32; ++l) M += lane_tot[l];
       if (M == 0) fail = true;
       const double q = P.q_ratio[jq];
-      rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
+      // upstream multiplies in T = float: values.size() * quantile (Matches.cpp getDistsQuantile)
+      rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)__fmul_rn((float)M, (float)q);
       if (M && rank >= M) rank = M - 1;
     }
     if (fail) {  // "no outlier to filter"
@@ -1179,7 +1180,7 @@ var_limit_kernel(const VarIn* __restrict__ in, const uint32_t* __restrict__ sort
     if (bi == 0x7fffffff) bi = min_el;
     const float ratio = __fdiv_rn((float)bi, (float)n);
     const double q = (double)ratio;
-    unsigned long long rank = (q == 1.0) ? (unsigned long long)(M - 1) : (unsigned long long)((double)M * q);
+    unsigned long long rank = (q == 1.0) ? (unsigned long long)(M - 1) : (unsigned long long)__fmul_rn((float)M, ratio);
     if (rank >= (unsigned long long)M) rank = M - 1;
     limit_out[blockIdx.x] = __uint_as_float(s[rank]);
     fail_out[blockIdx.x] = 0;
@@ -1547,7 +1548,7 @@ quantile_kernel(const float* __restrict__ d2, int64_t nk, double q, float* __res
         unsigned long long M = 0;
         for (int d = 0; d < 256; ++d) M += hist[d];
         if (M == 0) s_fail = 1;
-        rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)((double)M * q);
+        rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)__fmul_rn((float)M, (float)q);
         if (M && rank >= M) rank = M - 1;
       }
       unsigned long long cum = 0;

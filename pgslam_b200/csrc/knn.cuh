@@ -145,6 +145,37 @@ __device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float
   }
 }
 
+// The same for a K-list.  ncu on knn_kernel<10> (profiles/r2_knn10_blocks.md): 44 % of its warp
+// instructions were the eight unrolled 72-instruction insertions of a leaf scan, each running
+// with ~4 of 32 lanes - whichever lanes happened to accept THAT point.  Here every lane first
+// marks the points that beat its K-th key (8 distances, no insertion), then the lanes insert
+// their marked points together, one per trip: the insertion code exists once and runs as many
+// times as the lane with the most candidates needs (~3), not once per point slot (~6).
+template <int K>
+__device__ __forceinline__ void knn_scan_leaf(const TreeView& t, int leaf, float qx, float qy, float qz,
+                                              BestK<K>& acc, int skip_lo, int skip_hi) {
+  if (leaf >= t.n_leaves) return;
+  const float4* __restrict__ lp = t.pts + (size_t)leaf * kLeaf;
+  const int base = leaf * kLeaf;
+  const unsigned long long qxy = pack_f32x2(qx, qy);
+  const unsigned long long worst = acc.key[K - 1];
+  unsigned mask = 0u;
+#pragma unroll
+  for (int j = 0; j < kLeaf; ++j) {
+    const float4 p = __ldg(lp + j);
+    const unsigned long long nk = make_key(dist2_rn_packed(qxy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    const int pos = base + j;
+    if ((pos < skip_lo || pos > skip_hi) && nk < worst) mask |= 1u << j;
+  }
+#pragma unroll 1
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    const float4 p = __ldg(lp + j);
+    acc.offer(dist2_rn_packed(qxy, qz, p.x, p.y, p.z), __float_as_int(p.w), base + j);
+  }
+}
+
 // Exhaustive best-first walk of the subtree under `node` (at `depth`), whose own
 // box the caller has already accepted.  skip_lo..skip_hi: sorted positions the
 // caller has already offered (pass an empty range (0, -1) otherwise).

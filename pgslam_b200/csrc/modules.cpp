@@ -216,7 +216,7 @@ Module create_module(Kind kind, const std::string& name, const Params& params) {
     m.params[kv.first] = kv.second;
   }
   // `epsilon` != 0 asks libnabo for an APPROXIMATE search whose answer depends on libnabo's own
-  // tree shape and visit order (oracle/README.md: 8-49 % of the ids change, poses move by
+  // tree shape and visit order (measured with the CPU checker: 8-49 % of the ids change, poses move by
   // centimetres).  This library searches exactly; silently doing so would return results the
   // configuration did not ask for, so the parameter is refused unless the caller opts in.
   auto eps = m.params.find("epsilon");
