@@ -115,6 +115,10 @@ int pgs_matcher_knn(const pgs_matcher *m);
  * dist +inf; exact (eps = 0), ties -> lower index.                          */
 pgs_status pgs_matcher_find(pgs_matcher *m, const pgs_cloud *reading,
                             int32_t *ids, float *dists2, int on_device);
+/* Queries of the last pgs_matcher_find that the tensor-core distance-tile path
+ * (pgs_ctx_set_option "dense_max_ref") could not certify and answered with the
+ * exact fallback scan; needs option "dense_count_fallbacks" = 1.               */
+unsigned pgs_matcher_dense_fallbacks(const pgs_matcher *m);
 void pgs_matcher_destroy(pgs_matcher *m);
 
 /* ---- OutlierFilters (Localizer.hpp:330; LoopCloser.hpp:360) -------------- */
@@ -273,7 +277,9 @@ pgs_status pgs_ctx_set_profiling(pgs_ctx *ctx, int enabled);
 pgs_status pgs_ctx_set_batch_streams(pgs_ctx *ctx, int n_streams);
 pgs_status pgs_ctx_last_stage_times(const pgs_ctx *ctx, pgs_stage_times *out);
 /* Scheduling knobs of the hot kernels (never change a result): "match_mode"
- * 0..3, "pm_blocks", "pm_refill", "pm_pair_w", "pm_leaf_w" (DESIGN.md §6).     */
+ * 0..4, "pm_blocks", "pm_refill", "pm_pair_w", "pm_leaf_w", "mq_batches",
+ * "mq_blocks", "resort_it", "batch_chunk", "dense_max_ref",
+ * "dense_count_fallbacks" (DESIGN.md §6).                                      */
 pgs_status pgs_ctx_set_option(pgs_ctx *ctx, const char *key, double value);
 
 #ifdef __cplusplus

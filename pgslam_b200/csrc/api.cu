@@ -4,6 +4,7 @@
 #include <mutex>
 #include <thread>
 
+#include "dense.cuh"
 #include "filters.cuh"
 #include "icp.cuh"
 #include "modules.h"
@@ -24,6 +25,8 @@ struct pgs_matcher {
   Ctx* ctx;
   Module mod;
   std::unique_ptr<Index> index;
+  std::unique_ptr<DenseRef> dense;  // tensor-core tiles, built on first dense search
+  unsigned dense_fallbacks = 0;     // of the last dense search
 };
 struct pgs_outliers {
   Ctx* ctx;
@@ -177,6 +180,16 @@ void wire_icp(pgs_icp* icp) {
 void matcher_find(pgs_matcher* m, const Cloud& reading, int32_t* d_ids, float* d_d2) {
   if (!m->index) throw Error(PGS_INVALID_FIELD, "KDTreeMatcher: init() must be called before findClosests()");
   const int k = (int)m->mod.integer("knn");
+  // small reference clouds may take the tensor-core distance-tile path (option "dense_max_ref")
+  if (k == 1 && m->index->n > 0 && m->index->n <= std::min(m->ctx->tune.dense_max_ref, kDenseMaxRef)) {
+    if (!m->dense) {
+      m->dense = std::make_unique<DenseRef>();
+      dense_prepare(m->ctx, *m->index, *m->dense);
+    }
+    DenseQuery q{m->dense.get(), m->index->view(), reading.feat.p, (int)reading.n, d_ids, d_d2, nullptr, nullptr, nullptr};
+    m->dense_fallbacks = dense_knn1(m->ctx, {q}, (float)m->mod.real("maxDist"), m->ctx->tune.dense_count_fallbacks != 0);
+    return;
+  }
   KnnJob job{m->index->view(), reading.feat.p, nullptr, (int)reading.n, d_ids, d_d2};
   knn_batched(m->ctx, {job}, k, (float)m->mod.real("maxDist"));
 }
@@ -355,6 +368,8 @@ pgs_status pgs_ctx_set_option(pgs_ctx* ctx, const char* key, double value) {
   else if (k == "mq_batches") { if (v < 1 || v > 1024) throw Error(PGS_INVALID_ARGUMENT, "mq_batches must be 1..1024"); t.mq_batches = v; }
   else if (k == "mq_blocks") { t.mq_blocks = v; }
   else if (k == "resort_it") { t.resort_it = v; }
+  else if (k == "dense_max_ref") { t.dense_max_ref = v; }
+  else if (k == "dense_count_fallbacks") { t.dense_count_fallbacks = v; }
   else if (k == "batch_chunk") { if (v < 1 || v > 4096) throw Error(PGS_INVALID_ARGUMENT, "batch_chunk must be 1..4096"); t.batch_chunk = v; }
   else throw Error(PGS_INVALID_ARGUMENT, "pgs_ctx_set_option: unknown key " + k);
   PGS_API_END(&ctx->c)
@@ -546,8 +561,11 @@ pgs_status pgs_matcher_init(pgs_matcher* m, const pgs_cloud* reference) {
   std::vector<std::unique_ptr<Index>> idx;
   build_indices(m->ctx, {reference->c->feat.p}, {(int)reference->c->n}, nullptr, idx);
   m->index = std::move(idx[0]);
+  m->dense.reset();
   PGS_API_END(m->ctx)
 }
+
+unsigned pgs_matcher_dense_fallbacks(const pgs_matcher* m) { return m->dense_fallbacks; }
 
 int pgs_matcher_knn(const pgs_matcher* m) { return (int)m->mod.integer("knn"); }
 

@@ -75,6 +75,8 @@ Tuning::Tuning()
       mq_batches(env_int("PGS_MQ_BATCHES", 8)),
       mq_blocks(env_int("PGS_MQ_BLOCKS", 12)),
       resort_it(env_int("PGS_RESORT_IT", -1)),
+      dense_max_ref(env_int("PGS_DENSE_MAX_REF", 0)),
+      dense_count_fallbacks(env_int("PGS_DENSE_COUNT_FALLBACKS", 0)),
       batch_chunk(env_int("PGS_BATCH_CHUNK", 24)) {}
 
 Ctx* Ctx::worker(int i) {

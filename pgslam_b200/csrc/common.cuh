@@ -57,6 +57,9 @@ struct Tuning {
   int mq_batches;     // queue matcher (mode 4): batches of 32 queries per warp
   int mq_blocks;      // ... resident blocks per SM it is compiled for (10, 12 or 16)
   int resort_it;      // iteration after whose matches the reading is re-ordered by matched leaf (-1 never)
+  int dense_max_ref;  // KDTreeMatcher k = 1 on a reference of at most this many points uses the tensor-core
+                      // distance tiles (dense.cu) instead of the tree; 0 = never (default)
+  int dense_count_fallbacks;  // read back how many queries needed the exact fallback (one host sync)
   int batch_chunk;    // pairs per chunk a batch worker pulls (pgs_icp_run_batch)
   Tuning();
 };

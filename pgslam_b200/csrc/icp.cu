@@ -2127,6 +2127,23 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
     pm_ticket.reset(ctx, 1);
     pm_ticket.zero();
   }
+  // small references: tensor-core distance tiles instead of the tree (option "dense_max_ref")
+  DenseJobs dense_jobs;
+  bool use_dense = knn == 1 && ctx->tune.dense_max_ref > 0 && max_nr > 0;
+  for (int p = 0; p < P && use_dense; ++p)
+    use_dense = refs[p]->index->n > 0 && refs[p]->index->n <= std::min(ctx->tune.dense_max_ref, kDenseMaxRef);
+  if (use_dense) {
+    std::vector<DenseQuery> dq(P);
+    for (int p = 0; p < P; ++p) {
+      if (!refs[p]->dense) {
+        refs[p]->dense = std::make_unique<DenseRef>();
+        dense_prepare(ctx, *refs[p]->index, *refs[p]->dense);
+      }
+      dq[p] = DenseQuery{refs[p]->dense.get(), hv[p].tree, hv[p].reading, hv[p].n_r, nullptr, hv[p].match_d2, hv[p].match_pos,
+                         &d_states.p[p].xf, &d_states.p[p].active};
+    }
+    dense_upload_jobs(ctx, dq, dense_jobs);
+  }
   for (int it = 0; it < max_it; ++it) {
     if (*ctx->h_progress) break;
     if (it >= 2) {
@@ -2142,7 +2159,9 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
       kev.push_back(e);
     };
     mark();
-    if (knn == 1) {
+    if (use_dense) {
+      dense_launch(ctx, dense_jobs, prm.max_r2);
+    } else if (knn == 1) {
       if (match_mode == 0) {
         match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
       } else if (match_mode == 1) {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "core.cuh"
+#include "dense.cuh"
 #include "filters.cuh"
 #include "modules.h"
 
@@ -96,6 +97,8 @@ struct PreparedRef {
   // T_mean->p + T_mean_off, shared by the references prepared together
   std::shared_ptr<DBuf<double>> T_mean;
   size_t T_mean_off = 0;
+  // tensor-core distance tiles of a small reference (dense.cu), built on first use
+  mutable std::unique_ptr<DenseRef> dense;
 };
 
 // Where a batch's clouds come from.  fetch() makes the pairs [lo, hi) available on `ctx` and may

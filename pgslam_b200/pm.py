@@ -105,6 +105,7 @@ SIGNATURES = {
     "pgs_matcher_init": (C.c_int, [_vp, _vp]),
     "pgs_matcher_knn": (C.c_int, [_vp]),
     "pgs_matcher_find": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "pgs_matcher_dense_fallbacks": (C.c_uint, [_vp]),
     "pgs_matcher_destroy": (None, [_vp]),
     "pgs_outliers_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "pgs_outliers_append": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_int]),
@@ -486,6 +487,10 @@ class Matcher:
 
     def init(self, reference: DataPoints):
         self.ctx.check(self.ctx.lib.pgs_matcher_init(self.h, reference.h))
+
+    @property
+    def dense_fallbacks(self) -> int:
+        return int(self.ctx.lib.pgs_matcher_dense_fallbacks(self.h))
 
     def findClosests(self, reading: DataPoints) -> Matches:
         n, k = reading.getNbPoints(), self.knn
