@@ -161,36 +161,41 @@ def emit(line: dict, fd: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def leg_c3(pm, ctx, util, scans=200):
-    """BASELINE C3 in the small: sequential scan-to-map odometry through ICPSequence
-    (Localizer.hpp:103-126,148,254): every scan uploaded from the host, input filters, registration
-    against a 3-keyframe local map seeded with the previous pose, a new keyframe (local map rebuilt
-    on the device, setMap) every 10 scans.  One sequence is sequential: one GPU."""
-    from pgslam_b200 import synth
+def leg_c3(pm, ctx, util, dev, scans=2000):
+    """BASELINE C3: a 2000-scan odometry sequence through ICPSequence (Localizer.hpp:103-126,148,254):
+    every scan is uploaded from pinned host memory, run through the input filters, and registered
+    against a local map of up to 3 keyframes seeded with the previous pose; every 10th scan becomes
+    a keyframe (local map rebuilt on the device, setMap).  One sequence is sequential: one GPU."""
+    import torch
+    from pgslam_b200 import synth, synth_torch
     poses = synth.trajectory(scans + 1, step=0.25, turn_deg=1.0)
-    scene = synth.make_scene(77)
-    host = [np.ascontiguousarray(synth.velodyne_scan(77, 10 + i, poses[i], BEAMS, AZ, scene=scene).T) for i in range(24)]
+    dev_scans = synth_torch.trajectory_scans(77, poses, dev, beams=BEAMS, az_steps=AZ)
+    n_pts = BEAMS * AZ
+    host = torch.empty((scans + 1, n_pts, 4), dtype=torch.float32).pin_memory()
+    for i, t in enumerate(dev_scans):
+        host[i].copy_(t, non_blocking=True)
+    torch.cuda.synchronize()
+    del dev_scans
     filt = pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS), ctx=ctx)
     seq = pm.ICPSequence(ctx)
     seq.loadFromYaml(util.to_yaml(util.C2))
-    rigid = pm.RigidTransformation(ctx)
 
     def cloud(i):
-        c = pm.DataPoints(np.asfortranarray(host[i % len(host)].T), ctx=ctx)
+        c = pm.DataPoints(ctx=ctx, pinned_host_ptr=host[i].data_ptr(), n=n_pts)
         filt.apply(c)
         return c
     keyframes = [(cloud(0), np.eye(4))]
     seq.setMap(keyframes[0][0])
     T = np.eye(4)
-    lat, its = [], []
+    lat, its, fails = [], [], 0
     t_all = time.perf_counter()
     for i in range(1, scans + 1):
         t0 = time.perf_counter()
-        c = cloud(i % len(host))
+        c = cloud(i)
         try:
             T = seq(c, T)
         except pm.PointMatcherError:
-            T = np.eye(4)
+            fails += 1
         its.append(seq.last["iterations"])
         if i % 10 == 0:  # keyframe: local map = last 3 keyframes in the newest one's frame
             keyframes.append((c, T.copy()))
@@ -199,14 +204,17 @@ def leg_c3(pm, ctx, util, scans=200):
             m = pm.assemble_local_map([keyframes[-1][0]] + [k for k, _ in keyframes[:-1]],
                                       [np.eye(4)] + [Tn @ Tk for _, Tk in keyframes[:-1]])
             seq.setMap(m)
+            keyframes = [(k, Tn @ Tk) for k, Tk in keyframes]
             T = np.eye(4)
         lat.append(1e3 * (time.perf_counter() - t0))
     dt = time.perf_counter() - t_all
     lat.sort()
     return {"scans": scans, "scans_per_s": scans / dt, "latency_ms_p50": lat[len(lat) // 2],
             "latency_ms_p99": lat[min(len(lat) - 1, int(0.99 * len(lat)))], "iterations_mean": statistics.mean(its),
-            "note": "120k-pt scans from host memory, input filters (SurfaceNormal knn=10 + 3 more), ICPSequence against a "
-                    "local map of up to 3 keyframes (360k pts), keyframe + setMap every 10 scans"}
+            "failed_registrations": fails,
+            "note": "distinct 120k-pt scans along a trajectory, each uploaded from pinned host memory, input filters "
+                    "(SurfaceNormal knn=10 + 3 more), ICPSequence against a local map of up to 3 keyframes (360k pts), "
+                    "keyframe + local-map rebuild + setMap every 10 scans"}
 
 
 def leg_c5(pm, ctx, util, reps=5):
@@ -258,15 +266,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C5 / drop-in legs")
     ap.add_argument("--parity-pairs", type=int, default=16)
-    ap.add_argument("--batch-streams", type=int, default=8,
-                    help="worker streams the library splits a batch over (pgs_ctx_set_batch_streams)")
-    ap.add_argument("--batch-chunk", type=int, default=12, help="pairs per chunk a worker pulls")
+    ap.add_argument("--batch-streams", type=int, default=0,
+                    help="worker streams the library splits a batch over (0 = 8, or 4 when the ranks of the job "
+                         "would otherwise outnumber the host cores)")
+    ap.add_argument("--batch-chunk", type=int, default=0, help="pairs per chunk a worker pulls (0 = 96 / streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.batch_streams <= 0:
+        # every worker stream has a host thread (mostly asleep in its waits); 8 per rank measured best at
+        # N = 1, 4 per rank is what the 16-core box carried at N = 8 in round 1
+        args.batch_streams = 8 if world * 8 <= 2 * (os.cpu_count() or 16) else 4
+    if args.batch_chunk <= 0:
+        args.batch_chunk = 96 // args.batch_streams
 
     # ------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -494,7 +509,7 @@ def main():
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                    "one_thread": {"value": r1["value"], "cores": 1, "sample": r1["sample"]}}
         if not args.no_extras:
-            for name, fn in (("c3", lambda: leg_c3(pm, ctx, util)), ("c5", lambda: leg_c5(pm, ctx, util)), ("dropin", leg_dropin)):
+            for name, fn in (("c3", lambda: leg_c3(pm, ctx, util, dev)), ("c5", lambda: leg_c5(pm, ctx, util)), ("dropin", leg_dropin)):
                 try:
                     extras[name] = fn()
                 except Exception as e:  # extras never cost the headline line

@@ -1532,6 +1532,78 @@ static void yaw_to_T(double th, double tx, double ty, double tz, double *T) {
   T[12] = tx; T[13] = ty; T[14] = tz;
 }
 
+/* A.6 estimateCovariance (Censi) from the error elements and the transform just computed; order
+ * x,y,z,rx,ry,rz.  The estimate is the 6-DOF one whatever the solve was restricted to (upstream's
+ * PointToPlaneWithCov calls it on the result of compute_in_place).                              */
+static void censi_covariance(orc_min_out *out, double sensor_std_dev, const orc_cloud *reading,
+                             const orc_cloud *reference, const int32_t *ids, const float *d2,
+                             const float *w, int k) {
+  const int64_t nr = reading->n;
+    /* A.6 estimateCovariance (Censi), order x,y,z,rx,ry,rz              */
+    const double *T = out->T;
+    double beta = -asin(T[2]);
+    double alpha = atan2(T[6], T[10]);
+    double cb = cos(beta);
+    double gamma = atan2(T[1] / cb, T[0] / cb);
+    double t[3] = {T[12], T[13], T[14]};
+    double H[36], DD[36];
+    memset(H, 0, sizeof(H));
+    memset(DD, 0, sizeof(DD));
+    for (int64_t i = 0; i < nr; ++i)
+      for (int kk = 0; kk < k; ++kk) {
+        size_t m = (size_t)i * k + kk;
+        if (isinf(d2[m]) || w[m] == 0.f) continue;
+        const float *pf = reading->feat + 4 * i;
+        const float *qf = reference->feat + 4 * (int64_t)ids[m];
+        const float *nf = reference->normals + 3 * (int64_t)ids[m];
+        double p[3] = {pf[0], pf[1], pf[2]}, q[3] = {qf[0], qf[1], qf[2]};
+        double n[3] = {nf[0], nf[1], nf[2]};
+        double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        double rp = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        double rq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        if (!(nn > 0.0) || !(rp > 0.0) || !(rq > 0.0)) continue; /* degenerate pair */
+        for (int d = 0; d < 3; ++d) n[d] = n[d] / nn;
+        double dp[3] = {p[0] / rp, p[1] / rp, p[2] / rp};
+        double dq[3] = {q[0] / rq, q[1] / rq, q[2] / rq};
+        double na = n[2] * dp[1] - n[1] * dp[2];
+        double nb = n[0] * dp[2] - n[2] * dp[0];
+        double ng = n[1] * dp[0] - n[0] * dp[1];
+        double E = n[0] * (p[0] - gamma * p[1] + beta * p[2] + t[0] - q[0]);
+        E += n[1] * (gamma * p[0] + p[1] - alpha * p[2] + t[1] - q[1]);
+        E += n[2] * (-beta * p[0] + alpha * p[1] + p[2] + t[2] - q[2]);
+        double Np = n[0] * (dp[0] - gamma * dp[1] + beta * dp[2]);
+        Np += n[1] * (gamma * dp[0] + dp[1] - alpha * dp[2]);
+        Np += n[2] * (-beta * dp[0] + alpha * dp[1] + dp[2]);
+        double Nq = -(n[0] * dq[0] + n[1] * dq[1] + n[2] * dq[2]);
+        double g[6] = {n[0], n[1], n[2], rp * na, rp * nb, rp * ng};
+        double en = E + rp * Np;
+        double u[6] = {n[0] * Np, n[1] * Np, n[2] * Np, na * en, nb * en, ng * en};
+        double v[6] = {n[0] * Nq, n[1] * Nq, n[2] * Nq, rq * na * Nq, rq * nb * Nq, rq * ng * Nq};
+        for (int c = 0; c < 6; ++c)
+          for (int r = 0; r <= c; ++r) {
+            H[c * 6 + r] += g[c] * g[r];
+            DD[c * 6 + r] += u[c] * u[r] + v[c] * v[r];
+          }
+      }
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r < c; ++r) { H[r * 6 + c] = H[c * 6 + r]; DD[r * 6 + c] = DD[c * 6 + r]; }
+    double Hi[36], tmp[36];
+    inv6_sym(H, Hi);
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int kx = 0; kx < 6; ++kx) s += Hi[kx * 6 + r] * DD[c * 6 + kx];
+        tmp[c * 6 + r] = s;
+      }
+    double s2 = sensor_std_dev * sensor_std_dev;
+    for (int c = 0; c < 6; ++c)
+      for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+        for (int kx = 0; kx < 6; ++kx) s += tmp[kx * 6 + r] * Hi[c * 6 + kx];
+        out->cov[c * 6 + r] = s2 * s;
+      }
+  }
+
 int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_cloud *reading,
                     const orc_cloud *reference, const int32_t *ids, const float *d2,
                     const float *w, int k, orc_min_out *out) {
@@ -1540,7 +1612,11 @@ int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_c
   int64_t nr = reading->n;
   int p2plane = (type == ORC_E_POINT_TO_PLANE || type == ORC_E_POINT_TO_PLANE_WITH_COV);
   if (p2plane && !reference->normals) return ORC_INVALID_FIELD;
-  if (force_mode != ORC_FORCE_NONE && type != ORC_E_POINT_TO_PLANE) return ORC_INVALID_PARAMETER;
+  /* force2D / force4DOF: PointToPlane; force4DOF also with the covariance estimate (force2D cuts the
+   * error elements to 2-D upstream, which the 6-DOF covariance formula cannot take)                */
+  if (force_mode != ORC_FORCE_NONE && !(type == ORC_E_POINT_TO_PLANE ||
+                                        (type == ORC_E_POINT_TO_PLANE_WITH_COV && force_mode == ORC_FORCE_4DOF)))
+    return ORC_INVALID_PARAMETER;
   /* ErrorElements (A.4) */
   int64_t kept = 0;
   double wsum = 0.0;
@@ -1588,6 +1664,7 @@ int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_c
     double x[4] = {0, 0, 0, 0};
     solve_n(nd, A, b, x);
     yaw_to_T(x[0], x[1], x[2], force_mode == ORC_FORCE_4DOF ? x[3] : 0.0, out->T);
+    if (type == ORC_E_POINT_TO_PLANE_WITH_COV) censi_covariance(out, sensor_std_dev, reading, reference, ids, d2, w, k);
     return ORC_OK;
   }
 
@@ -1628,71 +1705,7 @@ int orc_minimize_ex(int type, int force_mode, double sensor_std_dev, const orc_c
     orc_solve6(A, b, x);
     angle_axis_to_T(x, out->T);
 
-    if (type == ORC_E_POINT_TO_PLANE_WITH_COV) {
-      /* A.6 estimateCovariance (Censi), order x,y,z,rx,ry,rz              */
-      const double *T = out->T;
-      double beta = -asin(T[2]);
-      double alpha = atan2(T[6], T[10]);
-      double cb = cos(beta);
-      double gamma = atan2(T[1] / cb, T[0] / cb);
-      double t[3] = {T[12], T[13], T[14]};
-      double H[36], DD[36];
-      memset(H, 0, sizeof(H));
-      memset(DD, 0, sizeof(DD));
-      for (int64_t i = 0; i < nr; ++i)
-        for (int kk = 0; kk < k; ++kk) {
-          size_t m = (size_t)i * k + kk;
-          if (isinf(d2[m]) || w[m] == 0.f) continue;
-          const float *pf = reading->feat + 4 * i;
-          const float *qf = reference->feat + 4 * (int64_t)ids[m];
-          const float *nf = reference->normals + 3 * (int64_t)ids[m];
-          double p[3] = {pf[0], pf[1], pf[2]}, q[3] = {qf[0], qf[1], qf[2]};
-          double n[3] = {nf[0], nf[1], nf[2]};
-          double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-          double rp = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-          double rq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-          if (!(nn > 0.0) || !(rp > 0.0) || !(rq > 0.0)) continue; /* degenerate pair */
-          for (int d = 0; d < 3; ++d) n[d] = n[d] / nn;
-          double dp[3] = {p[0] / rp, p[1] / rp, p[2] / rp};
-          double dq[3] = {q[0] / rq, q[1] / rq, q[2] / rq};
-          double na = n[2] * dp[1] - n[1] * dp[2];
-          double nb = n[0] * dp[2] - n[2] * dp[0];
-          double ng = n[1] * dp[0] - n[0] * dp[1];
-          double E = n[0] * (p[0] - gamma * p[1] + beta * p[2] + t[0] - q[0]);
-          E += n[1] * (gamma * p[0] + p[1] - alpha * p[2] + t[1] - q[1]);
-          E += n[2] * (-beta * p[0] + alpha * p[1] + p[2] + t[2] - q[2]);
-          double Np = n[0] * (dp[0] - gamma * dp[1] + beta * dp[2]);
-          Np += n[1] * (gamma * dp[0] + dp[1] - alpha * dp[2]);
-          Np += n[2] * (-beta * dp[0] + alpha * dp[1] + dp[2]);
-          double Nq = -(n[0] * dq[0] + n[1] * dq[1] + n[2] * dq[2]);
-          double g[6] = {n[0], n[1], n[2], rp * na, rp * nb, rp * ng};
-          double en = E + rp * Np;
-          double u[6] = {n[0] * Np, n[1] * Np, n[2] * Np, na * en, nb * en, ng * en};
-          double v[6] = {n[0] * Nq, n[1] * Nq, n[2] * Nq, rq * na * Nq, rq * nb * Nq, rq * ng * Nq};
-          for (int c = 0; c < 6; ++c)
-            for (int r = 0; r <= c; ++r) {
-              H[c * 6 + r] += g[c] * g[r];
-              DD[c * 6 + r] += u[c] * u[r] + v[c] * v[r];
-            }
-        }
-      for (int c = 0; c < 6; ++c)
-        for (int r = 0; r < c; ++r) { H[r * 6 + c] = H[c * 6 + r]; DD[r * 6 + c] = DD[c * 6 + r]; }
-      double Hi[36], tmp[36];
-      inv6_sym(H, Hi);
-      for (int c = 0; c < 6; ++c)
-        for (int r = 0; r < 6; ++r) {
-          double s = 0.0;
-          for (int kx = 0; kx < 6; ++kx) s += Hi[kx * 6 + r] * DD[c * 6 + kx];
-          tmp[c * 6 + r] = s;
-        }
-      double s2 = sensor_std_dev * sensor_std_dev;
-      for (int c = 0; c < 6; ++c)
-        for (int r = 0; r < 6; ++r) {
-          double s = 0.0;
-          for (int kx = 0; kx < 6; ++kx) s += tmp[kx * 6 + r] * Hi[c * 6 + kx];
-          out->cov[c * 6 + r] = s2 * s;
-        }
-    }
+    if (type == ORC_E_POINT_TO_PLANE_WITH_COV) censi_covariance(out, sensor_std_dev, reading, reference, ids, d2, w, k);
     return ORC_OK;
   }
 

@@ -1663,9 +1663,11 @@ int force_mode_of(const Module& minimizer) {
   if (minimizer.name == "PointToPointErrorMinimizer") return FORCE_NONE;
   const bool f2 = minimizer.flag("force2D"), f4 = minimizer.flag("force4DOF");
   if (!f2 && !f4) return FORCE_NONE;
-  if (minimizer.name == "PointToPlaneWithCovErrorMinimizer")
-    throw Error(PGS_INVALID_PARAMETER, "PointToPlaneWithCovErrorMinimizer: the covariance estimate is 6-DOF; "
-                                       "force2D / force4DOF are not supported with it");
+  // the covariance estimate is the 6-DOF one whatever the solve was restricted to; force2D cuts the
+  // error elements to 2-D upstream, which that formula cannot take
+  if (minimizer.name == "PointToPlaneWithCovErrorMinimizer" && f2)
+    throw Error(PGS_INVALID_PARAMETER, "PointToPlaneWithCovErrorMinimizer: force2D is not supported with the covariance "
+                                       "estimate (force4DOF is)");
   return f2 ? FORCE_2D : FORCE_4DOF;
 }
 

@@ -70,17 +70,47 @@ def _raycast(o, d, boxes, cyls):
     return best
 
 
+def _grids(dev, beams, az_steps):
+    el = torch.tensor(_elevations(beams), dtype=torch.float64, device=dev)
+    az = torch.tensor(np.linspace(0.0, 2 * np.pi, az_steps, endpoint=False), dtype=torch.float64, device=dev)
+    return az[:, None].expand(az_steps, beams), el[None, :].expand(az_steps, beams)  # azimuth-major, like a spinning sensor
+
+
+def _scans(dev, grids, rng_keys, Ts, boxes, cyls, beams, az_steps, range_noise, az_jitter_deg):
+    """One scan per entry: rng_keys[i] seeds scan i's jitter and noise, Ts[i] is its T_world_sensor,
+    boxes / cyls hold its scene.  Returns (B, N, 4) float32, {x,y,z,1} per point, sensor frame."""
+    azg0, elg = grids
+    n = beams * az_steps
+    jit, noise = [], []
+    for key in rng_keys:
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(key) & 0x7FFFFFFFFFFFFFFF)
+        jit.append(torch.rand((az_steps, beams), generator=g, dtype=torch.float64, device=dev))
+        noise.append(torch.randn((n,), generator=g, dtype=torch.float64, device=dev))
+    jitter = (torch.stack(jit) * 2.0 - 1.0) * np.deg2rad(az_jitter_deg)
+    azg = azg0[None] + jitter
+    ce = torch.cos(elg)[None]
+    ds = torch.stack([ce * torch.cos(azg), ce * torch.sin(azg), torch.sin(elg)[None].expand_as(azg)],
+                     dim=-1).reshape(len(rng_keys), n, 3)
+    Tt = torch.tensor(np.stack(Ts), dtype=torch.float64, device=dev)
+    # explicit sums, not a batched GEMM: the result must not depend on the batch size
+    R = Tt[:, :3, :3]
+    dw = torch.stack([ds[..., 0] * R[:, i, 0:1] + ds[..., 1] * R[:, i, 1:2] + ds[..., 2] * R[:, i, 2:3]
+                      for i in range(3)], dim=-1)
+    rng = _raycast(Tt[:, :3, 3], dw, boxes, cyls)
+    rng = torch.clamp(rng + torch.stack(noise) * range_noise, 1.0, 80.0)
+    pts = torch.ones((len(rng_keys), n, 4), dtype=torch.float32, device=dev)
+    pts[..., :3] = (ds * rng[..., None]).to(torch.float32)
+    return pts
+
+
 def scan_pairs(seeds, device, beams: int = 64, az_steps: int = 1875, range_noise: float = 0.02,
                az_jitter_deg: float = 0.02, chunk: int = 16):
     """[(reading, reference)] as (N, 4) float32 device tensors ({x,y,z,1} per point: the C ABI's
     layout) and the list of true T_ref_reading (numpy 4x4), one pair per seed."""
     dev = torch.device(device)
     seeds = [int(s) for s in seeds]
-    el = torch.tensor(_elevations(beams), dtype=torch.float64, device=dev)
-    az = torch.tensor(np.linspace(0.0, 2 * np.pi, az_steps, endpoint=False), dtype=torch.float64, device=dev)
-    azg0 = az[:, None].expand(az_steps, beams)  # azimuth-major, like a spinning sensor
-    elg = el[None, :].expand(az_steps, beams)
-    n = beams * az_steps
+    grids = _grids(dev, beams, az_steps)
     out, truths = [], []
     T_ref = synth.pose_matrix([0.0, 0.0, synth.SENSOR_HEIGHT])
     for c0 in range(0, len(seeds), chunk):
@@ -97,27 +127,24 @@ def scan_pairs(seeds, device, beams: int = 64, az_steps: int = 1875, range_noise
             truths.append(np.linalg.inv(T_ref) @ T_rd)
         clouds = {}
         for scan, Ts in ((0, [T_ref] * len(cs)), (1, poses)):
-            jit, noise = [], []
-            for s in cs:
-                g = torch.Generator(device=dev)
-                g.manual_seed((s * 2654435761 + 97 * scan + 12345) & 0x7FFFFFFFFFFFFFFF)
-                jit.append(torch.rand((az_steps, beams), generator=g, dtype=torch.float64, device=dev))
-                noise.append(torch.randn((n,), generator=g, dtype=torch.float64, device=dev))
-            jitter = (torch.stack(jit) * 2.0 - 1.0) * np.deg2rad(az_jitter_deg)
-            azg = azg0[None] + jitter
-            ce = torch.cos(elg)[None]
-            ds = torch.stack([ce * torch.cos(azg), ce * torch.sin(azg), torch.sin(elg)[None].expand_as(azg)],
-                             dim=-1).reshape(len(cs), n, 3)
-            Tt = torch.tensor(np.stack(Ts), dtype=torch.float64, device=dev)
-            # explicit sums, not a batched GEMM: the result must not depend on the batch size
-            R = Tt[:, :3, :3]
-            dw = torch.stack([ds[..., 0] * R[:, i, 0:1] + ds[..., 1] * R[:, i, 1:2] + ds[..., 2] * R[:, i, 2:3]
-                              for i in range(3)], dim=-1)
-            rng = _raycast(Tt[:, :3, 3], dw, boxes, cyls)
-            rng = torch.clamp(rng + torch.stack(noise) * range_noise, 1.0, 80.0)
-            pts = torch.ones((len(cs), n, 4), dtype=torch.float32, device=dev)
-            pts[..., :3] = (ds * rng[..., None]).to(torch.float32)
-            clouds[scan] = pts
+            keys = [s * 2654435761 + 97 * scan + 12345 for s in cs]
+            clouds[scan] = _scans(dev, grids, keys, Ts, boxes, cyls, beams, az_steps, range_noise, az_jitter_deg)
         for j in range(len(cs)):
             out.append((clouds[1][j].contiguous(), clouds[0][j].contiguous()))
     return out, truths
+
+
+def trajectory_scans(seed, poses, device, beams: int = 64, az_steps: int = 1875, range_noise: float = 0.02,
+                     az_jitter_deg: float = 0.02, chunk: int = 16):
+    """One scan per pose (T_world_sensor, numpy 4x4) of ONE scene (`seed`): the sequential-odometry
+    input of BASELINE config C3.  Returns a list of (N, 4) float32 device tensors, sensor frame."""
+    dev = torch.device(device)
+    grids = _grids(dev, beams, az_steps)
+    out = []
+    for c0 in range(0, len(poses), chunk):
+        Ts = poses[c0:c0 + chunk]
+        boxes, cyls = _scene_tensors([seed] * len(Ts), dev)
+        keys = [int(seed) * 2654435761 + 7919 * (c0 + j) + 777 for j in range(len(Ts))]
+        pts = _scans(dev, grids, keys, Ts, boxes, cyls, beams, az_steps, range_noise, az_jitter_deg)
+        out += [pts[j].contiguous() for j in range(len(Ts))]
+    return out

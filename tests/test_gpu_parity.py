@@ -1011,6 +1011,34 @@ def test_icp_point_to_plane_forced_modes(pm, pair30k, mode):
     assert e._last.residual == pytest.approx(ref_out["residual"], rel=1e-11)
 
 
+def test_icp_point_to_plane_with_cov_force4dof(pm, pair30k):
+    """force4DOF with the covariance estimate (F4 remainder): pose, iterations and the 6x6 Censi
+    covariance against the oracle; force2D stays rejected with the covariance."""
+    rd, rf, _ = pair30k
+    cfg = dict(util.C2, errorMinimizer={"PointToPlaneWithCovErrorMinimizer": {"force4DOF": 1, "sensorStdDev": 0.02}})
+    icp, T, want = _run_both(pm, cfg, rd, rf)
+    assert want["status"] == 0 and icp.last["iterations"] == want["iterations"]
+    util.assert_pose_close(T, want["T"])
+    np.testing.assert_allclose(T[2, :3], [0, 0, 1], atol=1e-12)
+    cov = icp.errorMinimizer.getCovariance()
+    np.testing.assert_allclose(cov, want["cov"], rtol=1e-6, atol=1e-16)
+    assert np.all(np.diag(cov) > 0)
+    bad = pm.ICP()
+    with pytest.raises(pm.InvalidParameter):
+        bad.loadFromYaml(util.to_yaml(dict(util.C2, errorMinimizer={"PointToPlaneWithCovErrorMinimizer": {"force2D": 1}})))
+
+
+def test_knn_k10_bit_exact_120k(pm, pair120k):
+    """k = 10 at full size (120k was k = 1 only): ids and distances against the oracle."""
+    rd, rf, _ = pair120k
+    m = pm.Matcher("KDTreeMatcher", {"knn": 10})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd))
+    ids, d2 = ob.kdtree_knn(rf, rd, k=10)
+    assert np.array_equal(got.ids, ids)
+    assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+
+
 # ------------------------------------------------ matcher scheduling variants ---
 def _bits(res):
     keys = ("T", "covariance", "iterations", "status", "overlap", "weighted_point_used_ratio", "point_used_ratio",
