@@ -1024,8 +1024,9 @@ def test_icp_point_to_plane_with_cov_force4dof(pm, pair30k):
     np.testing.assert_allclose(cov, want["cov"], rtol=1e-6, atol=1e-16)
     assert np.all(np.diag(cov) > 0)
     bad = pm.ICP()
-    with pytest.raises(pm.InvalidParameter):
-        bad.loadFromYaml(util.to_yaml(dict(util.C2, errorMinimizer={"PointToPlaneWithCovErrorMinimizer": {"force2D": 1}})))
+    bad.loadFromYaml(util.to_yaml(dict(util.C2, errorMinimizer={"PointToPlaneWithCovErrorMinimizer": {"force2D": 1}})))
+    with pytest.raises(pm.InvalidParameter):  # refused when the chain is instantiated for its first registration
+        bad(pm.DataPoints(rd), pm.DataPoints(rf))
 
 
 def test_knn_k10_bit_exact_120k(pm, pair120k):

@@ -39,3 +39,28 @@ for n in sizes:
     same = bool(torch.equal(res["tree"][1], res["dense"][1]))
     print(f"n_ref = n_query = {rf.shape[1]:6d}: tree {res['tree'][0]:8.1f} us/call, dense {res['dense'][0]:8.1f} us/call "
           f"(back-to-back calls, one stream), identical {same}", flush=True)
+
+# ---- the same inside the fused ICP loop: a batch of small pairs (loop-closure candidates on subsampled clouds)
+from tests import util  # noqa: E402
+for n in [s for s in sizes if s <= 8192]:
+    pairs = [synth.scan_pair(100 + i, beams=16, az_steps=max(8, n // 16))[:2] for i in range(48)]
+    rd = [pm.DataPoints(r, ctx=ctx) for r, _ in pairs]
+    rf = [pm.DataPoints(f, ctx=ctx) for _, f in pairs]
+    icp = pm.ICP(ctx)
+    icp.loadFromYaml(util.to_yaml(util.C2))
+    line = f"48 pairs of {pairs[0][0].shape[1]:5d}-pt clouds, C2 chain:"
+    sig = None
+    for name, dense in (("tree", 0), ("dense", 1 << 14)):
+        ctx.set_option("dense_max_ref", dense)
+        ctx.set_batch_streams(1)
+        for _ in range(2):
+            icp.compute_batch_array(rd, rf)
+        ctx.set_profiling(True)
+        rec = icp.compute_batch_array(rd, rf)
+        st = ctx.stage_times()
+        ctx.set_profiling(False)
+        sig = sig or rec.tobytes()
+        line += f"  {name}: match {st['match_ms']:.3f} ms of loop {st['loop_ms']:.3f} ms ({st['iterations_launched']} launches)"
+        same = rec.tobytes() == sig
+    print(line + f"  identical {same}", flush=True)
+ctx.set_option("dense_max_ref", 0)
