@@ -156,6 +156,26 @@ def cpu_reference_run(steps, warmup, sample_pairs=1, threads=None):
                        f"serial (copies, quantile, minimizer)")
 
 
+def resolve_batching(args, world):
+    if args.batch_streams <= 0:
+        # every worker stream has a host thread (mostly asleep in its waits); 8 per rank measured best at
+        # N = 1, 4 per rank is what the 16-core box carried at N = 8 in round 1
+        args.batch_streams = 8 if world * 8 <= 2 * (os.cpu_count() or 16) else 4
+    if args.batch_chunk <= 0:
+        args.batch_chunk = 96 // args.batch_streams
+
+
+def make_config(args, world):
+    """the `config` object of the JSON line: identical for the GPU arm and the reference arm"""
+    per = -(-args.pool // world)
+    in_bytes = 2 * per * BEAMS * AZ * 16
+    return {"workload": WORKLOAD, "pool_pairs": args.pool, "pairs_per_gpu_per_step": per,
+            "points_per_scan": BEAMS * AZ, "batch_streams": args.batch_streams, "batch_chunk": args.batch_chunk,
+            "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
+            "parallelism": f"{world} GPU(s), contiguous blocks of the pool per rank, NCCL all_gather of the result records",
+            "pool_generator": "pgslam_b200/synth_torch.py on the device, pair i <- seed i"}
+
+
 def emit(line: dict, fd: int):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
@@ -276,12 +296,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.batch_streams <= 0:
-        # every worker stream has a host thread (mostly asleep in its waits); 8 per rank measured best at
-        # N = 1, 4 per rank is what the 16-core box carried at N = 8 in round 1
-        args.batch_streams = 8 if world * 8 <= 2 * (os.cpu_count() or 16) else 4
-    if args.batch_chunk <= 0:
-        args.batch_chunk = 96 // args.batch_streams
+    resolve_batching(args, args.gpus if args.impl == "reference" else world)
 
     # ------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -292,8 +307,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 points / f64 reductions",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pool_pairs": args.pool, "points_per_scan": BEAMS * AZ,
-                           "step": "one registration of the workload per step (bounded sample of the pool)"},
+                "config": make_config(args, max(args.gpus, 1)),
+                "reference_step": "one registration of the workload per step (bounded sample of the pool), all host threads",
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "iterations": r["iterations"]}
@@ -333,6 +348,9 @@ def main():
     for c0 in range(0, B, 32):
         seeds = [mine[j] for j in range(c0, min(B, c0 + 32))]
         data, _ = synth_torch.scan_pairs(seeds, dev, beams=BEAMS, az_steps=AZ)
+        # the library copies on ITS stream (non-blocking: no implicit ordering with torch's): the generator's
+        # kernels must have finished before the clouds are handed over
+        torch.cuda.synchronize()
         for j, (rd, rf) in enumerate(data):
             dev_rd.append(pm.DataPoints(ctx=ctx, device_ptr=rd.data_ptr(), n=n_pts))
             dev_rf.append(pm.DataPoints(ctx=ctx, device_ptr=rf.data_ptr(), n=n_pts))
@@ -518,11 +536,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 points / f64 reductions", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pool_pairs": POOL, "pairs_per_gpu_per_step": len(pdist.shard_range(POOL, 0, world)),
-                       "points_per_scan": n_pts, "batch_streams": args.batch_streams, "batch_chunk": args.batch_chunk,
-                       "l2_policy": f"inputs larger than L2: {in_bytes / 1e6:.0f} MB of distinct clouds per GPU per step",
-                       "parallelism": f"{world} GPU(s), contiguous blocks of the pool per rank, NCCL all_gather of the result records",
-                       "pool_generator": "pgslam_b200/synth_torch.py on the device, pair i <- seed i"},
+            "config": make_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes * world,
                     "d2h_bytes_per_step": int(POOL * 480), "ms_per_step": ms_e2e / args.steps,
                     "entry": "pgs_icp_run_batch_multi (host-resident pairs, pinned), chunked uploads inside the call",
