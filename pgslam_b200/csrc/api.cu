@@ -549,7 +549,7 @@ pgs_status pgs_matcher_create(pgs_ctx* ctx, const char* name, const char* const*
   auto h = std::make_unique<pgs_matcher>();
   h->ctx = &ctx->c;
   h->mod = create_module(Kind::Matcher, name, kv_params(kv, nkv));
-  if (h->mod.integer("knn") > 32) throw Error(PGS_INVALID_PARAMETER, "KDTreeMatcher: knn > 32 is not supported");
+  if (h->mod.integer("knn") > 256) throw Error(PGS_INVALID_PARAMETER, "KDTreeMatcher: knn > 256 is not supported");
   *out = h.release();
   PGS_API_END(&ctx->c)
 }

@@ -459,7 +459,7 @@ void voxel_grid(Ctx* ctx, const Module& m, Cloud& c) {
 
 void surface_normals(Ctx* ctx, const Module& m, std::vector<Cloud*>& clouds) {
   const int k = (int)m.integer("knn");
-  if (k > 32) throw Error(PGS_INVALID_PARAMETER, "SurfaceNormalDataPointsFilter: knn > 32 is not supported");
+  if (k > kMaxDynK) throw Error(PGS_INVALID_PARAMETER, "SurfaceNormalDataPointsFilter: knn > 256 is not supported");
   const float max_dist = (float)m.real("maxDist");
   // upstream smooths in place, point after point, so every normal depends on the already
   // smoothed normals of lower-indexed neighbours: an order-dependent recurrence with no

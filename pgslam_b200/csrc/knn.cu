@@ -67,6 +67,38 @@ knn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
   }
 }
 
+// knn > 32: run-time k, keys in local memory (BestDyn)
+__global__ void __launch_bounds__(128)
+knn_dyn_kernel(const KnnJobDev* __restrict__ jobs, int k, float maxr2) {
+  const KnnJobDev job = jobs[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= job.nq) return;
+  const float4 q = job.queries[j];
+  unsigned long long keys[kMaxDynK];
+  BestDyn acc{keys, k};
+  acc.init(maxr2);
+  if (job.self) {
+    // neighbours in tree order are mostly neighbours in space: the +-k window gives a bound
+    // before the tree is touched, then the climb from the query's own leaf
+    const int skip_lo = max(0, j - k), skip_hi = min(job.tree.n - 1, j + k);
+    for (int p = skip_lo; p <= skip_hi; ++p) {
+      const float4 c = job.tree.pts[p];
+      acc.offer(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), p);
+    }
+    knn_climb(job.tree, j / kLeaf, q.x, q.y, q.z, acc, skip_lo, skip_hi);
+  } else {
+    knn_traverse(job.tree, q.x, q.y, q.z, acc);
+  }
+  const int col = job.self ? __float_as_int(q.w) : (job.qperm ? job.qperm[j] : j);
+  int32_t* oi = job.ids + (size_t)col * k;
+  float* od = job.d2 ? job.d2 + (size_t)col * k : nullptr;
+  for (int e = 0; e < k; ++e) {
+    const int id = key_id(keys[e]);
+    oi[e] = (id == 0x7fffffff) ? -1 : id;
+    if (od) od[e] = (id == 0x7fffffff) ? __int_as_float(0x7f800000) : key_dist(keys[e]);
+  }
+}
+
 template <int K>
 void launch_k(Ctx* ctx, dim3 grid, const KnnJobDev* d_jobs, int k, float maxr2) {
   knn_kernel<K><<<grid, 128, 0, ctx->stream>>>(d_jobs, k, maxr2);
@@ -74,7 +106,7 @@ void launch_k(Ctx* ctx, dim3 grid, const KnnJobDev* d_jobs, int k, float maxr2) 
 
 void launch(Ctx* ctx, const std::vector<KnnJobDev>& jobs, int k, float max_dist) {
   if (jobs.empty()) return;
-  if (k < 1 || k > 32) throw Error(PGS_INVALID_PARAMETER, "knn must be in [1, 32]");
+  if (k < 1 || k > kMaxDynK) throw Error(PGS_INVALID_PARAMETER, "knn must be in [1, " + std::to_string(kMaxDynK) + "]");
   int max_q = 0;
   for (auto& j : jobs) max_q = std::max(max_q, j.nq);
   if (max_q == 0) return;
@@ -95,7 +127,8 @@ void launch(Ctx* ctx, const std::vector<KnnJobDev>& jobs, int k, float max_dist)
   else if (k <= 16) launch_k<16>(ctx, grid, d_jobs.p, k, maxr2);
   else if (k <= 20) launch_k<20>(ctx, grid, d_jobs.p, k, maxr2);
   else if (k <= 24) launch_k<24>(ctx, grid, d_jobs.p, k, maxr2);
-  else launch_k<32>(ctx, grid, d_jobs.p, k, maxr2);
+  else if (k <= 32) launch_k<32>(ctx, grid, d_jobs.p, k, maxr2);
+  else knn_dyn_kernel<<<grid, 128, 0, ctx->stream>>>(d_jobs.p, k, maxr2);
   ctx_count_launches(ctx, 1);
   PGS_LAUNCH_CHECK();
 }

@@ -76,6 +76,29 @@ struct BestK {
   }
 };
 
+// K-list of run-time length (knn > 32): the keys live in local memory and an insertion shifts
+// with a loop.  Slower than the register lists above - it exists so that a libpointmatcher
+// configuration with a large `knn` (SurfaceNormal on sparse clouds) runs at all.
+constexpr int kMaxDynK = 256;
+struct BestDyn {
+  unsigned long long* key;  // k entries, ascending
+  int k;
+  __device__ __forceinline__ void init(float maxr2) {
+    for (int j = 0; j < k; ++j) key[j] = make_key(maxr2, 0x7fffffff);
+  }
+  __device__ __forceinline__ float bound() const { return key_dist(key[k - 1]); }
+  __device__ __forceinline__ void offer(float dd, int iid, int) {
+    const unsigned long long nk = make_key(dd, iid);
+    if (nk >= key[k - 1]) return;
+    int j = k - 1;
+    while (j > 0 && key[j - 1] > nk) {
+      key[j] = key[j - 1];
+      --j;
+    }
+    key[j] = nk;
+  }
+};
+
 // Batcher's odd-even merge sort of 16 keys held in registers (63 compare-exchanges, checked
 // with the 0-1 principle by the generator): every index is a literal, so the array never
 // leaves the register file.

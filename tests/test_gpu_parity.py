@@ -1092,3 +1092,24 @@ def test_match_modes_batch_with_ragged_pairs(pm, ctx, mode):
             assert _bits(a) == _bits(b)
     finally:
         ctx.set_option("match_mode", 0)
+
+
+@pytest.mark.parametrize("k", [33, 64, 100])
+def test_knn_above_32_matcher_and_surface_normals(pm, pair30k, k):
+    """knn > 32 (F4 remainder): the run-time K-list path, against the oracle bit for bit."""
+    rd, rf, _ = pair30k
+    rd, rf = rd[:, :6000], rf[:, :9000]
+    m = pm.Matcher("KDTreeMatcher", {"knn": k})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd))
+    ids, d2 = ob.kdtree_knn(rf, rd, k=k)
+    assert np.array_equal(got.ids, ids)
+    assert np.array_equal(got.dists.view(np.uint32), d2.view(np.uint32))
+    if k <= 64:
+        dp = pm.DataPoints(rf)
+        f = pm.DataPointsFilters()
+        f.append("SurfaceNormalDataPointsFilter", {"knn": k, "keepDensities": 1})
+        f.apply(dp)
+        oc = ob.Cloud(rf)
+        ob.apply_filter(oc, "SurfaceNormalDataPointsFilter", knn=k, keepDensities=1)
+        _cmp_cloud(dp, oc)
