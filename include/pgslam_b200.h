@@ -83,6 +83,13 @@ pgs_status pgs_cloud_copy(const pgs_cloud *c, pgs_cloud **out);  /* DP copy-ctor
 /* DP::concatenate (LocalMap.hpp:222): keeps descriptors common to both      */
 pgs_status pgs_cloud_concatenate(pgs_cloud *a, const pgs_cloud *b);
 void pgs_cloud_destroy(pgs_cloud *c);
+/* DataPoints::load / DataPoints::save (static members of PM::DataPoints): libpointmatcher's
+ * .csv, legacy ASCII .vtk and .ply (ascii or binary on load) files, by extension.  Columns
+ * x y z -> features; nx ny nz -> "normals"; name_x name_y name_z -> span-3 descriptor `name`.
+ * pgs_cloud_file_info parses a file on the host only (no device): point and descriptor counts. */
+pgs_status pgs_cloud_load(pgs_ctx *ctx, const char *path, pgs_cloud **out);
+pgs_status pgs_cloud_save(const pgs_cloud *c, const char *path);
+pgs_status pgs_cloud_file_info(const char *path, int64_t *n_points, int *n_descriptors, char *err, int cap);
 
 /* ---- Transformation (Localizer.hpp:20,106; LocalMap.hpp:97,222) ---------- */
 /* PM::get().REG(Transformation).create("RigidTransformation")->compute():

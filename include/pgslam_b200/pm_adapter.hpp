@@ -459,6 +459,30 @@ struct PointMatcher {
     }
     void dropDeviceCopy() const { dev_.reset(); }
 
+    // DataPoints::load / save: libpointmatcher's .csv, legacy ASCII .vtk and .ply files (pgs_cloud_load / _save)
+    static DataPoints load(const std::string& fileName) {
+      CtxPtr ctx = context();
+      auto d = std::make_shared<detail::DeviceCloud>();
+      d->ctx = ctx;
+      check(pgs_cloud_load(ctx->h, fileName.c_str(), &d->h), ctx);
+      DataPoints out;
+      out.adopt(d);
+      return out;
+    }
+    void save(const std::string& fileName) const {
+      if (times.rows() > 0) {  // the file formats carry no times (and must not carry the index column)
+        DataPoints plain = *this;
+        plain.times = Int64Matrix();
+        plain.timeLabels.clear();
+        plain.dropDeviceCopy();
+        plain.save(fileName);
+        return;
+      }
+      CtxPtr ctx = context();
+      auto d = device(ctx);
+      check(pgs_cloud_save(d->h, fileName.c_str()), d->ctx);
+    }
+
    private:
     mutable DevicePtr dev_;
   };

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libpgslam_b200.so")
-SOURCES = ["cloud.cu", "sort.cu", "index.cu", "kdorder.cu", "knn.cu", "dense.cu", "filters.cu", "icp.cu", "api.cu", "modules.cpp"]
+SOURCES = ["cloud.cu", "sort.cu", "index.cu", "kdorder.cu", "knn.cu", "dense.cu", "filters.cu", "icp.cu", "api.cu", "modules.cpp", "cloud_io.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

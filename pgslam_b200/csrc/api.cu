@@ -4,6 +4,7 @@
 #include <mutex>
 #include <thread>
 
+#include "cloud_io.h"
 #include "dense.cuh"
 #include "filters.cuh"
 #include "icp.cuh"
@@ -477,6 +478,68 @@ void pgs_cloud_destroy(pgs_cloud* c) {
     delete c;
   } catch (...) {
   }
+}
+
+pgs_status pgs_cloud_load(pgs_ctx* ctx, const char* path, pgs_cloud** out) {
+  PGS_API_BEGIN(&ctx->c)
+  if (!path || !out) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_load: bad arguments");
+  HostCloud hc;
+  load_cloud_file(path, hc);
+  auto h = std::make_unique<pgs_cloud>();
+  h->c = std::make_unique<Cloud>(&ctx->c);
+  h->c->n = hc.n;
+  h->c->feat.reset(&ctx->c, (size_t)hc.n);
+  copy_in(&ctx->c, h->c->feat.p, hc.features.data(), (size_t)hc.n * sizeof(float4), 0);
+  for (auto& d : hc.descs) {
+    Desc& dd = h->c->add(d.label, d.span);
+    copy_in(&ctx->c, dd.data.p, d.data.data(), d.data.size() * sizeof(float), 0);
+  }
+  *out = h.release();
+  PGS_API_END(&ctx->c)
+}
+
+pgs_status pgs_cloud_save(const pgs_cloud* c, const char* path) {
+  Ctx* ctx = c->c->ctx;
+  PGS_API_BEGIN(ctx)
+  if (!path) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_save: path is NULL");
+  c->c->wait_ready();
+  HostCloud hc;
+  hc.n = c->c->n;
+  hc.features.resize((size_t)hc.n * 4);
+  copy_out(ctx, hc.features.data(), c->c->feat.p, (size_t)hc.n * sizeof(float4), 0);
+  for (auto& d : c->c->descs) {
+    HostDesc hd;
+    hd.label = d.label;
+    hd.span = d.span;
+    hd.data.resize((size_t)hc.n * d.span);
+    copy_out(ctx, hd.data.data(), d.data.p, hd.data.size() * sizeof(float), 0);
+    hc.descs.push_back(std::move(hd));
+  }
+  save_cloud_file(path, hc);
+  PGS_API_END(ctx)
+}
+
+pgs_status pgs_cloud_file_info(const char* path, int64_t* n_points, int* n_descriptors, char* err, int cap) {
+  int code = PGS_OK;
+  std::string msg;
+  try {
+    if (!path) throw Error(PGS_INVALID_ARGUMENT, "pgs_cloud_file_info: path is NULL");
+    HostCloud hc;
+    load_cloud_file(path, hc);
+    if (n_points) *n_points = hc.n;
+    if (n_descriptors) *n_descriptors = (int)hc.descs.size();
+  } catch (const pgs::Error& ex) {
+    code = ex.code;
+    msg = ex.what();
+  } catch (const std::exception& ex) {
+    code = PGS_INVALID_ARGUMENT;
+    msg = ex.what();
+  }
+  if (err && cap > 0) {
+    std::strncpy(err, msg.c_str(), cap - 1);
+    err[cap - 1] = '\0';
+  }
+  return (pgs_status)code;
 }
 
 // ---- Transformation -------------------------------------------------------------

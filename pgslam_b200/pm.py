@@ -93,6 +93,9 @@ SIGNATURES = {
     "pgs_cloud_copy": (C.c_int, [_vp, C.POINTER(_vp)]),
     "pgs_cloud_concatenate": (C.c_int, [_vp, _vp]),
     "pgs_cloud_destroy": (None, [_vp]),
+    "pgs_cloud_load": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "pgs_cloud_save": (C.c_int, [_vp, C.c_char_p]),
+    "pgs_cloud_file_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "pgs_rigid_transform": (C.c_int, [_vp, _dp]),
     "pgs_cloud_assemble": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _dp, C.POINTER(_vp)]),
     "pgs_filters_create_from_yaml": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
@@ -202,6 +205,17 @@ def available_parameters(kind: str, name: str) -> list[dict]:
         out.append(dict(name=f[0].value.decode(), doc=f[1].value.decode(), default=f[2].value.decode(),
                         min=f[3].value.decode(), max=f[4].value.decode(), type=t.value.decode()))
     return out
+
+
+def cloud_file_info(path: str) -> tuple[int, int]:
+    """(points, descriptors) of a csv / vtk / ply file, parsed on the host (no device needed)."""
+    L = load_library()
+    n, nd = C.c_int64(0), C.c_int(0)
+    err = C.create_string_buffer(512)
+    st = L.pgs_cloud_file_info(os.fsencode(path), C.byref(n), C.byref(nd), err, 512)
+    if st != OK:
+        raise _EXC.get(st, PointMatcherError)(st, err.value.decode())
+    return int(n.value), int(nd.value)
 
 
 def _mat(T):
@@ -361,15 +375,15 @@ class DataPoints:
 
     @classmethod
     def load(cls, path: str, ctx: "Context | None" = None) -> "DataPoints":
-        """DataPoints::load (csv / vtk / ply, by extension): host parse, one upload."""
-        from . import cloud_io as _io
-        feats, desc = _io.load(path)
-        return cls(feats, desc or None, ctx=ctx)
+        """DataPoints::load (csv / vtk / ply, by extension) through the C ABI (pgs_cloud_load)."""
+        ctx = ctx or default_context()
+        h = _vp()
+        ctx.check(ctx.lib.pgs_cloud_load(ctx.h, os.fsencode(path), C.byref(h)))
+        return cls(ctx=ctx, _handle=h)
 
     def save(self, path: str):
-        """DataPoints::save (csv / vtk / ply, by extension)."""
-        from . import cloud_io as _io
-        _io.save(path, self.features, self.descriptors())
+        """DataPoints::save (csv / vtk / ply, by extension) through the C ABI (pgs_cloud_save)."""
+        self.ctx.check(self.ctx.lib.pgs_cloud_save(self.h, os.fsencode(path)))
 
     def copy(self) -> "DataPoints":
         h = _vp()

@@ -319,6 +319,16 @@ int main(int argc, char** argv) {
         for (int r = 0; r < 4; ++r) same &= res[i].transformation(r, c) == res2[i].transformation(r, c);
     std::printf("batch_two_contexts_equal=%d\n", same);
   }
+  {
+    // DataPoints::save / load (csv) next to the input file
+    const std::string path = std::string(argv[1]) + ".roundtrip.csv";
+    input_cloud.save(path);
+    DP back = DP::load(path);
+    int same = back.getNbPoints() == input_cloud.getNbPoints() && back.descriptorLabels.size() == input_cloud.descriptorLabels.size();
+    for (int i = 0; same && i < static_cast<int>(back.features.cols()); i += 37)
+      same = back.features(0, i) == input_cloud.features(0, i) && back.descriptors(1, i) == input_cloud.descriptors(1, i);
+    std::printf("file_roundtrip=%d\n", same);
+  }
   run_typed<double>(input_cloud, candidate_cloud, icp_config_buffer_, "T_double");
   return 0;
 }

@@ -91,6 +91,7 @@ def test_pgslam_call_sites_run_and_match_the_oracle(tmp_path):
     assert np.array_equal(Tb, T) and int(kv["batch_iterations0"]) == want["iterations"]
     assert int(kv["batch_converged"]) == 1 and int(kv["batch_two_contexts_equal"]) == 1
     assert int(kv["batch_pair2_status"]) == ob.icp_run(cfg, orf, orf)["status"]
+    assert int(kv["file_roundtrip"]) == 1
     # T = double: the pose is returned in double, not through float
     Td = np.array([float(x) for x in kv["T_double"].split(",")]).reshape(4, 4).T
     assert np.abs(Td - want["T"]).max() < 1e-9 and not np.array_equal(Td, Td.astype(np.float32).astype(np.float64))

@@ -634,6 +634,33 @@ def test_cloud_files_as_libpointmatcher_writes_them(tmp_path):
         cloud_io.load(str(tmp_path / "x.pcd"))
 
 
+def test_c_abi_cloud_file_parser_on_the_host(tmp_path):
+    """pgs_cloud_file_info: the C ABI's csv / vtk / ply parser (pgs_cloud_load without the upload) reads the
+    files the Python module writes, and libpointmatcher-style files, with the same point / descriptor counts."""
+    from pgslam_b200 import cloud_io
+    g = np.random.default_rng(1)
+    n = 129
+    feats = np.vstack([g.normal(size=(3, n)).astype(np.float32), np.ones((1, n), np.float32)])
+    desc = {"normals": g.normal(size=(3, n)).astype(np.float32), "simpleSensorNoise": g.random((1, n)).astype(np.float32),
+            "observationDirections": g.normal(size=(3, n)).astype(np.float32), "eigValues": g.random((3, n)).astype(np.float32)}
+    for ext in ("csv", "vtk", "ply"):
+        path = str(tmp_path / f"c.{ext}")
+        cloud_io.save(path, feats, desc)
+        assert pm.cloud_file_info(path) == (n, 4)
+    p = tmp_path / "lpm.csv"
+    p.write_text("x,y,z,nx,ny,nz,intensity\n1,2,3,0,0,1,0.5\n4,5,6,1,0,0,0.25\n")
+    assert pm.cloud_file_info(str(p)) == (2, 2)
+    p = tmp_path / "bare.csv"
+    p.write_text("1 2 3\n4 5 6\n7 8 9\n")
+    assert pm.cloud_file_info(str(p)) == (3, 0)
+    with pytest.raises(pm.PointMatcherError):
+        pm.cloud_file_info(str(tmp_path / "x.pcd"))
+    p = tmp_path / "noz.csv"
+    p.write_text("x,y\n1,2\n")
+    with pytest.raises(pm.PointMatcherError, match="'z' column"):
+        pm.cloud_file_info(str(p))
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on
     stdout with the contract's keys; the GPU arm refuses to run without a device instead of falling back."""

@@ -1113,3 +1113,40 @@ def test_knn_above_32_matcher_and_surface_normals(pm, pair30k, k):
         oc = ob.Cloud(rf)
         ob.apply_filter(oc, "SurfaceNormalDataPointsFilter", knn=k, keepDensities=1)
         _cmp_cloud(dp, oc)
+
+
+@pytest.mark.parametrize("ext", ["csv", "vtk", "ply"])
+def test_cloud_files_through_the_c_abi(pm, pair30k, tmp_path, ext):
+    """DataPoints::load / save in the C ABI (pgs_cloud_load / pgs_cloud_save, F4 remainder): a filtered cloud
+    written by the library is read back bit for bit by the library AND by the independent Python parser,
+    and a file written by the Python module loads to the same cloud."""
+    from pgslam_b200 import cloud_io
+    rd, _, _ = pair30k
+    dp = pm.DataPoints(rd[:, :3000])
+    f = pm.DataPointsFilters(util.to_yaml(util.INPUT_FILTERS))
+    f.apply(dp)
+    path = str(tmp_path / f"a.{ext}")
+    dp.save(path)
+    feats, desc = cloud_io.load(path)
+    assert np.array_equal(feats, dp.features) and set(desc) == set(dp.descriptors)
+    for k, v in dp.descriptors.items():
+        assert np.array_equal(desc[k], v), k
+    back = pm.DataPoints.load(path)
+    assert np.array_equal(back.features, dp.features)
+    assert {k: v.tobytes() for k, v in back.descriptors.items()} == {k: v.tobytes() for k, v in dp.descriptors.items()}
+    path2 = str(tmp_path / f"b.{ext}")
+    cloud_io.save(path2, dp.features, dp.descriptors)
+    again = pm.DataPoints.load(path2)
+    assert np.array_equal(again.features, dp.features) and again.getNbPoints() == 3000
+    if ext == "ply":  # binary little-endian PLY, as other tools write it
+        n = 100
+        rec = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("intensity", "<u1")])
+        rec["x"], rec["y"], rec["z"], rec["intensity"] = np.arange(n), 2 * np.arange(n), -np.arange(n), np.arange(n) % 250
+        p3 = tmp_path / "bin.ply"
+        with open(p3, "wb") as fh:
+            fh.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 100\nproperty float x\nproperty float y\n"
+                     b"property float z\nproperty uchar intensity\nend_header\n")
+            fh.write(rec.tobytes())
+        c = pm.DataPoints.load(str(p3))
+        assert c.getNbPoints() == n and np.array_equal(c.features[1], 2 * np.arange(n, dtype=np.float32))
+        assert np.array_equal(c.getDescriptorByName("intensity")[0], (np.arange(n) % 250).astype(np.float32))
