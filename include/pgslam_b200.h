@@ -248,6 +248,12 @@ pgs_status pgs_icp_probe_residual(pgs_icp *icp, const pgs_cloud *reading,
  * number of modules the configuration instantiates.                          */
 pgs_status pgs_config_check(const char *yaml, size_t len, int is_chain,
                             int *n_modules, char *err, int cap);
+/* Where a VALID configuration still departs from what libpointmatcher would do with it, in
+ * words (one line per item, NUL-terminated into `out`; returns the number of items):
+ * stochastic filters in readingStepDataPointsFilters (drawn once per registration here, once per
+ * iteration upstream), `epsilon` accepted under PGS_EPSILON_POLICY=exact, seeds of the
+ * counter-based generator.  Host only.                                                         */
+int pgs_config_warnings(const char *yaml, size_t len, int is_chain, char *out, int cap);
 /* Registrar introspection: number of registered modules of a kind
  * (0 DataPointsFilter, 1 Matcher, 2 OutlierFilter, 3 ErrorMinimizer,
  * 4 TransformationChecker, 5 Inspector, 6 Logger, 7 Transformation) and the

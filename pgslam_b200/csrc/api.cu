@@ -286,6 +286,50 @@ pgs_status pgs_config_check(const char* yaml, size_t len, int is_chain, int* n_m
   return (pgs_status)code;
 }
 
+int pgs_config_warnings(const char* yaml, size_t len, int is_chain, char* out, int cap) {
+  std::vector<std::string> w;
+  try {
+    auto stochastic = [](const Module& m) {
+      return m.name == "RandomSamplingDataPointsFilter" || m.name == "MaxDensityDataPointsFilter" ||
+             (m.name == "SamplingSurfaceNormalDataPointsFilter" && m.integer("samplingMethod") == 0);
+    };
+    auto scan = [&](const std::vector<Module>& mods, const char* where, bool step) {
+      for (auto& m : mods) {
+        if (stochastic(m)) {
+          w.push_back(std::string(where) + ": " + m.name + " draws from a counter-based hash of (seed, point index), not from rand(): "
+                      "same distribution, reproducible, different points than libpointmatcher keeps");
+          if (step)
+            w.push_back(std::string(where) + ": " + m.name + " is applied ONCE per registration; libpointmatcher re-applies the step "
+                        "filters to a fresh copy of the reading every iteration, so its random subset changes per iteration");
+        }
+        auto e = m.params.find("epsilon");
+        if (e != m.params.end() && m.name != "ShadowDataPointsFilter" && std::atof(e->second.c_str()) != 0.0)
+          w.push_back(std::string(where) + ": " + m.name + " epsilon = " + e->second + " accepted under PGS_EPSILON_POLICY=exact: the "
+                      "search is exact, libnabo's would be approximate");
+      }
+    };
+    const YamlNode root = parse_yaml(std::string(yaml, len));
+    if (is_chain) {
+      ChainConfig c = chain_from_yaml(std::string(yaml, len));
+      scan(c.reading_filters, "readingDataPointsFilters", false);
+      scan(c.reading_step_filters, "readingStepDataPointsFilters", true);
+      scan(c.reference_filters, "referenceDataPointsFilters", false);
+      scan({c.matcher}, "matcher", false);
+    } else {
+      scan(module_list_from_yaml(Kind::DataPointsFilter, root), "filters", false);
+    }
+  } catch (const std::exception& ex) {
+    w.push_back(std::string("configuration rejected: ") + ex.what());
+  }
+  std::string text;
+  for (auto& s : w) text += s + "\n";
+  if (out && cap > 0) {
+    std::strncpy(out, text.c_str(), cap - 1);
+    out[cap - 1] = '\0';
+  }
+  return (int)w.size();
+}
+
 int pgs_registrar_count(int kind) {
   if (kind < 0 || kind > 7) return 0;
   return (int)registered_modules((Kind)kind).size();

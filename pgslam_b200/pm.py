@@ -136,6 +136,7 @@ SIGNATURES = {
     "pgs_icp_probe_overlap": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "pgs_icp_probe_residual": (C.c_int, [_vp, _vp, _vp, _dp, _dp]),
     "pgs_config_check": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "pgs_config_warnings": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_int]),
     "pgs_registrar_count": (C.c_int, [C.c_int]),
     "pgs_registrar_name": (C.c_char_p, [C.c_int, C.c_int]),
     "pgs_registrar_param_count": (C.c_int, [C.c_int, C.c_char_p]),
@@ -181,6 +182,15 @@ def check_config(yaml_text: str, chain: bool = True) -> int:
     if st != OK:
         raise _EXC.get(st, PointMatcherError)(st, err.value.decode())
     return n.value
+
+
+def config_warnings(yaml_text: str, chain: bool = True) -> list[str]:
+    """Where a valid configuration still departs from libpointmatcher's behaviour (pgs_config_warnings)."""
+    L = load_library()
+    b = yaml_text.encode()
+    buf = C.create_string_buffer(4096)
+    L.pgs_config_warnings(b, len(b), int(chain), buf, 4096)
+    return [ln for ln in buf.value.decode().splitlines() if ln]
 
 
 def registered(kind: str) -> list[str]:

@@ -634,6 +634,17 @@ def test_cloud_files_as_libpointmatcher_writes_them(tmp_path):
         cloud_io.load(str(tmp_path / "x.pcd"))
 
 
+def test_config_warnings_name_the_departures_from_upstream():
+    assert pm.config_warnings(util.to_yaml(util.C2)) == []
+    cfg = dict(util.C2, readingStepDataPointsFilters=[{"RandomSamplingDataPointsFilter": {"prob": 0.5}}],
+               readingDataPointsFilters=[{"MaxDensityDataPointsFilter": {"maxDensity": 50}}])
+    w = pm.config_warnings(util.to_yaml(cfg))
+    assert len(w) == 3 and any("ONCE per registration" in x for x in w) and sum("counter-based hash" in x for x in w) == 2
+    w = pm.config_warnings("- RandomSamplingDataPointsFilter: {prob: 0.3}\n", chain=False)
+    assert len(w) == 1 and "rand()" in w[0]
+    assert "rejected" in pm.config_warnings("matcher:\n  NoSuchMatcher\n")[0]
+
+
 def test_c_abi_cloud_file_parser_on_the_host(tmp_path):
     """pgs_cloud_file_info: the C ABI's csv / vtk / ply parser (pgs_cloud_load without the upload) reads the
     files the Python module writes, and libpointmatcher-style files, with the same point / descriptor counts."""
