@@ -405,7 +405,7 @@ pgs_status pgs_ctx_set_option(pgs_ctx* ctx, const char* key, double value) {
   const std::string k(key);
   Tuning& t = ctx->c.tune;
   const int v = (int)value;
-  if (k == "match_mode") { if (v < 0 || v > 4) throw Error(PGS_INVALID_ARGUMENT, "match_mode must be 0..4"); t.match_mode = v; }
+  if (k == "match_mode") { if (v < 0 || v > 5) throw Error(PGS_INVALID_ARGUMENT, "match_mode must be 0..5"); t.match_mode = v; }
   else if (k == "pm_blocks") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_blocks must be 1..32"); t.pm_blocks = v; }
   else if (k == "pm_refill") { if (v < 1 || v > 32) throw Error(PGS_INVALID_ARGUMENT, "pm_refill must be 1..32"); t.pm_refill = v; }
   else if (k == "pm_pair_w") { if (v < 1) throw Error(PGS_INVALID_ARGUMENT, "pm_pair_w must be >= 1"); t.pm_pair_w = v; }

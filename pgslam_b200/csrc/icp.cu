@@ -682,6 +682,32 @@ match_persistent_kernel(const PairView* __restrict__ views, PairState* __restric
   }
 }
 
+// match_kernel with the seed-path search (knn_seed_path): one sibling box per level instead of the
+// two child boxes of a descent, no separate climb.
+__global__ void PGS_MATCH_BOUNDS
+match_path_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, float maxr2) {
+  PairState& st = states[blockIdx.y];
+  if (!st.active) return;
+  const PairView v = views[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_r) return;
+  const Xf T = st.xf;
+  float4 r = v.reading[i];
+  float3 q = xform_rn(T, r.x, r.y, r.z);
+  Best1 acc;
+  acc.init(maxr2);
+  const int pp = st.iterations > 0 ? v.match_pos[i] : -1;
+  if (pp >= 0) {
+    const float4 c = __ldg(v.tree.pts + pp);
+    acc.offer(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_int(c.w), pp);
+    knn_seed_path(v.tree, pp / kLeaf, q.x, q.y, q.z, acc);
+  } else {
+    knn_traverse(v.tree, q.x, q.y, q.z, acc);
+  }
+  v.match_pos[i] = acc.pos;
+  v.match_d2[i] = acc.dist();
+}
+
 // ---------------------------------------------------------------------------
 // Queue matcher.  ncu on match_kernel (profiles/r2_match_blocks.md): the first descent and the
 // first leaf scan run with all 32 lanes, everything after them - revisits of pending siblings,
@@ -2168,6 +2194,8 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
         match_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
       } else if (match_mode == 1) {
         match_cells_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
+      } else if (match_mode == 5) {
+        match_path_kernel<<<gm, 128, 0, s>>>(d_views.p, d_states.p, prm.max_r2);
       } else if (match_mode == 4) {
         const int mq_batches = std::max(1, ctx->tune.mq_batches);
         const dim3 gq(ceil_div(std::max(max_nr, 1), 128 * mq_batches), P);

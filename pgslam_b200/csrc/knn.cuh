@@ -242,6 +242,79 @@ __device__ __forceinline__ void knn_traverse_from(const TreeView& t, unsigned no
   }
 }
 
+// The walk of knn_traverse_from, entered at its walk-back stage: (node, depth) is a node that has
+// been dealt with and `trail` marks the pending siblings above it (bit g = the sibling of the
+// ancestor g levels up still has to be looked at).
+template <class Acc>
+__device__ __forceinline__ void knn_traverse_resume(const TreeView& t, unsigned node, int depth, unsigned trail, float qx,
+                                                    float qy, float qz, Acc& acc) {
+  const ulonglong2* __restrict__ nodes16 = reinterpret_cast<const ulonglong2*>(t.nodes);
+  const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
+  const QueryPk q = pack_query(qx, qy, qz);
+  while (true) {
+    // ---- walk back to the deepest pending sibling whose box still qualifies --
+    while (true) {
+      if (trail == 0) return;
+      const int up = __ffs(trail) - 1;
+      node >>= up;
+      depth -= up;
+      trail >>= up;
+      node ^= 1u;
+      trail ^= 1u;
+      const unsigned long long* __restrict__ nb = nodes8 + (size_t)node * 3;
+      if (box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2)) <= acc.bound()) break;
+    }
+    // ---- descend while the nearer child qualifies -------------------------
+    bool at_leaf = true;
+    while (depth < t.depth) {
+      const ulonglong2* __restrict__ c = nodes16 + (size_t)node * 3;
+      const ulonglong2 a = __ldg(c), b = __ldg(c + 1), e = __ldg(c + 2);
+      const float lb0 = box_lb_packed(q, a.x, a.y, b.x);
+      const float lb1 = box_lb_packed(q, b.y, e.x, e.y);
+      const float bound = acc.bound();
+      const bool near1 = lb1 < lb0;
+      const float lbn = near1 ? lb1 : lb0, lbf = near1 ? lb0 : lb1;
+      if (!(lbn <= bound)) { at_leaf = false; break; }
+      trail = (trail << 1) | ((lbf <= bound) ? 1u : 0u);
+      node = node * 2 + (near1 ? 1u : 0u);
+      ++depth;
+    }
+    if (at_leaf) knn_scan_leaf(t, (int)node - t.P, qx, qy, qz, acc, 0, -1);
+  }
+}
+
+// Seeded search along the seed leaf's own path: the sibling of every ancestor of the seed leaf is
+// tested ONCE against the bound the caller already has (one 24-byte box per level, addresses known
+// from the leaf index alone, four loads in flight), which yields the pending-sibling trail a
+// descent from the root would have built on its way to the seed leaf - without testing the boxes
+// ON the path (the seed leaf is scanned whatever they say) and without the dependent loads of a
+// descent.  Then the seed leaf is scanned and the walk continues as knn_traverse_from would.
+template <class Acc>
+__device__ __forceinline__ void knn_seed_path(const TreeView& t, int leaf, float qx, float qy, float qz, Acc& acc) {
+  const unsigned long long* __restrict__ nodes8 = reinterpret_cast<const unsigned long long*>(t.nodes);
+  const QueryPk q = pack_query(qx, qy, qz);
+  const unsigned node = (unsigned)(t.P + leaf);
+  const float bound = acc.bound();
+  unsigned trail = 0u;
+  for (int g = 0; g < t.depth; g += 4) {
+    float lbv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lbv[u] = __int_as_float(0x7f800000);
+      if (g + u < t.depth) {
+        const unsigned sib = (node >> (g + u)) ^ 1u;
+        const unsigned long long* __restrict__ nb = nodes8 + (size_t)sib * 3;
+        lbv[u] = box_lb_packed(q, __ldg(nb), __ldg(nb + 1), __ldg(nb + 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (g + u < t.depth && lbv[u] <= bound) trail |= 1u << (g + u);
+  }
+  knn_scan_leaf(t, leaf, qx, qy, qz, acc, 0, -1);
+  knn_traverse_resume(t, node, t.depth, trail, qx, qy, qz, acc);
+}
+
 // top-down search from the root (no prior knowledge about the query)
 template <class Acc>
 __device__ __forceinline__ void knn_traverse(const TreeView& t, float qx, float qy, float qz,

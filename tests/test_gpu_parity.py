@@ -1047,7 +1047,7 @@ def _bits(res):
     return [np.asarray(res[k]).tobytes() for k in keys]
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_match_modes_give_bit_identical_registrations(pm, ctx, pair30k, mode):
     """The cell-guided and persistent matchers (pgs_ctx_set_option "match_mode") must return the
     same exact nearest neighbours as the default one: whole results compared bit for bit."""
@@ -1076,7 +1076,7 @@ def test_match_modes_give_bit_identical_registrations(pm, ctx, pair30k, mode):
         ctx.set_option("match_mode", 0)
 
 
-@pytest.mark.parametrize("mode", [1, 3, 4])
+@pytest.mark.parametrize("mode", [1, 3, 4, 5])
 def test_match_modes_batch_with_ragged_pairs(pm, ctx, mode):
     """A batch of pairs of different sizes through the persistent matcher: ranges of inactive /
     short pairs are skipped, results equal the default matcher's bit for bit."""
