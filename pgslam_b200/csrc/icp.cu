@@ -990,7 +990,6 @@ __global__ void __launch_bounds__(256)
 select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ states, IcpParams P, int jq, int pass,
                    int* n_active, volatile int* h_done) {
   __shared__ unsigned hist[kSelBins];
-  __shared__ unsigned lane_tot[32];
   __shared__ bool last;
   PairState& st = states[blockIdx.y];
   if (!st.active) return;
@@ -1039,51 +1038,65 @@ select_pass_kernel(const PairView* __restrict__ views, PairState* __restrict__ s
     v.sel_hist[d] = 0;
   }
   __syncthreads();
-  if (tid < 32) {
-    unsigned t = 0;
-    for (int d = lane * 64; d < lane * 64 + 64; ++d) t += hist[d];
-    lane_tot[lane] = t;
+  // the digit that holds the wanted rank, found by the first warp: lane l owns bins 64l .. 64l+63
+  if (tid >= 32) return;
+  unsigned t = 0;
+  for (int d = lane * 64; d < lane * 64 + 64; ++d) t += hist[d];
+  unsigned incl = t;  // inclusive prefix over the lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
   }
-  __syncthreads();
-  if (tid == 0) {
-    st.ticket3 = 0;
-    unsigned long long rank = st.sel_rank;
-    bool fail = false;
-    if (pass == 0) {
-      unsigned long long M = 0;
-      for (int l = 0; l < 32; ++l) M += lane_tot[l];
-      if (M == 0) fail = true;
-      const double q = P.q_ratio[jq];
-      // upstream multiplies in T = float: values.size() * quantile (Matches.cpp getDistsQuantile)
-      rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)__fmul_rn((float)M, (float)q);
-      if (M && rank >= M) rank = M - 1;
-    }
-    if (fail) {  // "no outlier to filter"
+  const unsigned M = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long rank = st.sel_rank;
+  if (pass == 0) {
+    const double q = P.q_ratio[jq];
+    // upstream multiplies in T = float: values.size() * quantile (Matches.cpp getDistsQuantile)
+    rank = (q == 1.0) ? (M ? M - 1 : 0) : (unsigned long long)__fmul_rn((float)M, (float)q);
+    if (M && rank >= M) rank = M - 1;
+  }
+  if (pass == 0 && M == 0) {  // "no outlier to filter"
+    if (lane == 0) {
+      st.ticket3 = 0;
       st.status = PGS_CONVERGENCE_ERROR;
       st.active = 0;
       pair_finished(n_active, h_done);
-    } else {
-      unsigned long long cum = 0;
-      int l = 0;
-      for (; l < 31; ++l) {
-        if (cum + lane_tot[l] > rank) break;
-        cum += lane_tot[l];
-      }
-      int d = l * 64;
-      for (; d < l * 64 + 63; ++d) {
-        if (cum + hist[d] > rank) break;
-        cum += hist[d];
-      }
-      st.sel_rank = rank - cum;
-      const unsigned np = prefix | ((unsigned)d << shift);
-      st.sel_prefix = np;
-      st.sel_mask = mask | (dmask << shift);
-      if (pass == 2) {
-        const float limit = __fmul_rn(P.q_factor[jq], __uint_as_float(np));
-        const float hi = jq == 0 ? P.fixed_hi : st.lim_hi;
-        st.lim_hi = fminf(hi, limit);
-        st.lim_lo = P.fixed_lo;
-      }
+    }
+    return;
+  }
+  // first lane whose inclusive count exceeds the rank (the last lane if none does)
+  const unsigned over = __ballot_sync(0xffffffffu, (unsigned long long)incl > rank);
+  const int l = over ? __ffs(over) - 1 : 31;
+  const unsigned before = __shfl_sync(0xffffffffu, incl - t, l);
+  // inside that lane's 64 bins: two bins per lane
+  const unsigned h0 = hist[l * 64 + 2 * lane], h1 = hist[l * 64 + 2 * lane + 1];
+  unsigned inc2 = h0 + h1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned up = __shfl_up_sync(0xffffffffu, inc2, o);
+    if (lane >= o) inc2 += up;
+  }
+  const unsigned long long rel = rank - before;  // rank inside lane l's bins
+  const unsigned over2 = __ballot_sync(0xffffffffu, (unsigned long long)inc2 > rel);
+  const int l2 = over2 ? __ffs(over2) - 1 : 31;
+  if (lane == l2) {
+    const unsigned ex2 = inc2 - (h0 + h1);
+    // the last bin of the range is taken when nothing exceeds the rank (cannot happen for a
+    // consistent histogram; kept as the bound the serial scan had)
+    const bool second = over2 ? ((unsigned long long)ex2 + h0 <= rel) : true;
+    const int d = l * 64 + 2 * lane + (second ? 1 : 0);
+    const unsigned cum = before + ex2 + (second ? h0 : 0u);
+    st.ticket3 = 0;
+    st.sel_rank = rank - cum;
+    const unsigned np = prefix | ((unsigned)d << shift);
+    st.sel_prefix = np;
+    st.sel_mask = mask | (dmask << shift);
+    if (pass == 2) {
+      const float limit = __fmul_rn(P.q_factor[jq], __uint_as_float(np));
+      const float hi = jq == 0 ? P.fixed_hi : st.lim_hi;
+      st.lim_hi = fminf(hi, limit);
+      st.lim_lo = P.fixed_lo;
     }
   }
 }
@@ -2146,7 +2159,10 @@ void IcpEngine::run_prepared(const std::vector<const Cloud*>& readings, const st
   std::vector<cudaEvent_t> kev;  // profiling only: 4 marks per iteration
   const int max_it = prm.hard_iteration_cap;
   const dim3 gm(ceil_div(std::max(max_nr, 1), 128), P), ga(acc_blocks, P);
-  const dim3 gs(std::max(1, std::min(kSelBlocks, ceil_div(max_nm, 2048))), P);
+  // the quantile select is an exact order statistic, so its grid may follow the batch: about four
+  // blocks per SM over all pairs (a lone pair gets one load trip per thread instead of eight)
+  const int sel_blocks = std::max(kSelBlocks, ceil_div(4 * ctx->num_sms, std::max(P, 1)));
+  const dim3 gs(std::max(1, std::min(sel_blocks, ceil_div(max_nm, 1024))), P);
   if (prm.n_quant == 0) {
     fixed_limits_kernel<<<ceil_div(P, 64), 64, 0, s>>>(d_states.p, prm, P);
     ctx_count_launches(ctx, 1);

@@ -117,10 +117,15 @@ gather_sorted_kernel(const BuildJob* __restrict__ jobs, const float* __restrict_
   job.dst[j] = o;
 }
 
+// Leaf boxes, and the kLeafLevels tree levels above them: a block owns an aligned run of 256
+// leaves, so the subtree over them is reduced in shared memory without leaving the block.
+constexpr int kLeafLevels = 8;  // log2 of leaf_box_kernel's block size
 __global__ void __launch_bounds__(256) leaf_box_kernel(const BuildJob* __restrict__ jobs) {
+  __shared__ float sb[2][256][6];
   const BuildJob job = jobs[blockIdx.y];
-  const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-  if (leaf >= job.P) return;
+  const int first = blockIdx.x * 256;
+  if (first >= job.P) return;
+  const int leaf = first + threadIdx.x;
   const float inf = __int_as_float(0x7f800000);
   float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   if (leaf < job.n_leaves) {
@@ -135,17 +140,39 @@ __global__ void __launch_bounds__(256) leaf_box_kernel(const BuildJob* __restric
       }
     }
   }
-  float* nd = job.nodes + (size_t)(job.P + leaf) * 6;
   // node layout {lo.x, lo.y, hi.x, hi.y, lo.z, hi.z}: three 8-byte halves that feed the
   // packed fp32x2 box test (box_lb_packed) straight from the load
-  nd[0] = lo[0]; nd[1] = lo[1]; nd[2] = hi[0];
-  nd[3] = hi[1]; nd[4] = lo[2]; nd[5] = hi[2];
+  float* me = sb[0][threadIdx.x];
+  me[0] = lo[0]; me[1] = lo[1]; me[2] = hi[0];
+  me[3] = hi[1]; me[4] = lo[2]; me[5] = hi[2];
+  if (leaf < job.P) {
+    float* nd = job.nodes + (size_t)(job.P + leaf) * 6;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) nd[e] = me[e];
+  }
+  const int span = min(256, job.P);  // leaves of this block
+  int cur = 0;
+  for (int k = 1; (span >> k) >= 1; ++k) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < (span >> k)) {
+      const float* a = sb[cur][2 * t];
+      const float* b = sb[cur][2 * t + 1];
+      float* o = sb[cur ^ 1][t];
+      o[0] = fminf(a[0], b[0]); o[1] = fminf(a[1], b[1]); o[4] = fminf(a[4], b[4]);
+      o[2] = fmaxf(a[2], b[2]); o[3] = fmaxf(a[3], b[3]); o[5] = fmaxf(a[5], b[5]);
+      float* nd = job.nodes + (size_t)(((job.P + first) >> k) + t) * 6;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) nd[e] = o[e];
+    }
+    cur ^= 1;
+  }
 }
 
-// one block per job walks the levels bottom-up
-__global__ void __launch_bounds__(1024) upper_levels_kernel(const BuildJob* __restrict__ jobs) {
+// the levels above leaf_box_kernel's: one block per job walks them bottom-up
+__global__ void __launch_bounds__(64) upper_levels_kernel(const BuildJob* __restrict__ jobs) {
   const BuildJob job = jobs[blockIdx.x];
-  for (int width = job.P >> 1; width >= 1; width >>= 1) {
+  for (int width = job.P >> (kLeafLevels + 1); width >= 1; width >>= 1) {
     for (int i = threadIdx.x; i < width; i += blockDim.x) {
       const int node = width + i;
       const float* a = job.nodes + (size_t)(2 * node) * 6;
@@ -301,8 +328,11 @@ void build_indices(Ctx* ctx, const std::vector<const float4*>& d_pts, const std:
   ctx_count_launches(ctx, 1);
   if (want_boxes) {
     leaf_box_kernel<<<dim3(ceil_div(max_P, 256), B), 256, 0, s>>>(d_jobs.p);
-    upper_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
-    ctx_count_launches(ctx, 2);
+    ctx_count_launches(ctx, 1);
+    if (max_P > (1 << kLeafLevels)) {
+      upper_levels_kernel<<<B, 64, 0, s>>>(d_jobs.p);
+      ctx_count_launches(ctx, 1);
+    }
     if (out[0]->cells.p) {
       cell_levels_kernel<<<B, 1024, 0, s>>>(d_jobs.p);
       ctx_count_launches(ctx, 1);
