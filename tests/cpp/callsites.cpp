@@ -122,6 +122,7 @@ static int bench_main(int n) {
     icp_.loadFromYaml(iss);
   }
   double best = 1e30, best_cached = 1e30, first = 0;
+  double ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // phases of the best cold repetition
   int iterations = 0;
   for (int rep = 0; rep < 6; ++rep) {
     if (rep < 3) {  // cold: new host data every time, as for a new keyframe
@@ -129,8 +130,11 @@ static int bench_main(int n) {
       candidate_cloud.features(0, 0) += 1e-3f;
     }
     const double t0 = now_ms();
+    double tp[9];
+    tp[0] = t0;
     // ProcessVertex (LoopCloser.hpp:98)
     Matrix T = icp_(input_cloud, candidate_cloud, Matrix::Identity(4, 4));
+    tp[1] = now_ms();
     // CheckIcpResult (LoopCloser.hpp:308-340)
     volatile bool reached = icp_.getMaxNumIterationsReached();
     volatile float overlap = icp_.errorMinimizer->getOverlap();
@@ -139,25 +143,37 @@ static int bench_main(int n) {
     TY::ICP temp_icp;
     std::istringstream iss{yaml};
     temp_icp.loadFromYaml(iss);
+    tp[2] = now_ms();
     DP reading(input_cloud);
     temp_icp.transformations.apply(reading, T);
+    tp[3] = now_ms();
     DP reference(candidate_cloud);
     temp_icp.referenceDataPointsFilters.apply(reference);
+    tp[4] = now_ms();
     temp_icp.matcher->init(reference);
+    tp[5] = now_ms();
     auto matches = temp_icp.matcher->findClosests(reading);
+    tp[6] = now_ms();
     auto w = temp_icp.outlierFilters.compute(reading, reference, matches);
+    tp[7] = now_ms();
     volatile float residual = temp_icp.errorMinimizer->getResidualError(reading, reference, w, matches);
     (void)residual;
-    const double dt = now_ms() - t0;
+    tp[8] = now_ms();
+    const double dt = tp[8] - t0;
     if (rep == 0) first = dt;
-    else if (rep < 3) best = std::min(best, dt);
-    else best_cached = std::min(best_cached, dt);
+    else if (rep < 3) {
+      if (dt < best)
+        for (int i = 0; i < 8; ++i) ph[i] = tp[i + 1] - tp[i];
+      best = std::min(best, dt);
+    } else best_cached = std::min(best_cached, dt);
     iterations = icp_.lastResult().iterations;
   }
   std::printf("{\"dropin_ms\": %.3f, \"dropin_ms_unchanged_clouds\": %.3f, \"first_call_ms\": %.3f, \"points\": %d, "
-              "\"iterations\": %d, \"sequence\": \"LoopCloser::ProcessVertex + CheckIcpResult + ComputeResidualError "
+              "\"iterations\": %d, \"phases_ms\": {\"icp\": %.3f, \"checks_and_yaml\": %.3f, \"copy_transform\": %.3f, "
+              "\"reference_filters\": %.3f, \"matcher_init\": %.3f, \"find_closests\": %.3f, \"outlier_weights\": %.3f, "
+              "\"residual\": %.3f}, \"sequence\": \"LoopCloser::ProcessVertex + CheckIcpResult + ComputeResidualError "
               "through pm_adapter.hpp, host DataPoints in, host results out\"}\n",
-              best, best_cached, first, n, iterations);
+              best, best_cached, first, n, iterations, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
   return 0;
 }
 
