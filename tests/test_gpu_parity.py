@@ -878,6 +878,29 @@ def test_icp_empty_clouds_are_convergence_errors(pm, pair30k):
     assert m.findClosests(pm.DataPoints(empty)).ids.shape == (2, 0)
 
 
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_icp_with_nan_points_follows_the_oracle(pm, pair30k, name):
+    """No RemoveNaN filter in the chain: NaN reading points never match and the registration goes on;
+    NaN reference points poison the reference mean, which is a convergence error on both sides."""
+    rd, rf, _ = pair30k
+    g = np.random.default_rng(1)
+    bad = g.choice(rd.shape[1], 40, replace=False)
+    rdn, rfn = rd.copy(), rf.copy()
+    rdn[g.integers(0, 3, bad.size), bad] = np.nan
+    rfn[g.integers(0, 3, bad.size), bad] = np.nan
+    cfgd = getattr(util, name)
+    want = ob.icp_run(ob.config_from_dict(cfgd), ob.Cloud(rdn), ob.Cloud(rf))
+    assert want["status"] == 0
+    icp = pm.ICP()
+    icp.loadFromYaml(util.to_yaml(cfgd))
+    T = icp(pm.DataPoints(rdn), pm.DataPoints(rf))
+    assert icp.last["iterations"] == want["iterations"]
+    np.testing.assert_allclose(T, want["T"], atol=1e-9)
+    assert ob.icp_run(ob.config_from_dict(cfgd), ob.Cloud(rd), ob.Cloud(rfn))["status"] != 0
+    with pytest.raises(pm.ConvergenceError):
+        icp(pm.DataPoints(rd), pm.DataPoints(rfn))
+
+
 def test_icp_with_matcher_max_dist_and_filter_chain(pm, pair30k):
     """maxDist on the matcher leaves unmatched points (id -1, dist inf) that every later
     stage has to skip the same way; several outlier filters multiply."""

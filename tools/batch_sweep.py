@@ -48,7 +48,7 @@ host_rd = [r.cpu().pin_memory() for r, _ in data]
 host_rf = [f.cpu().pin_memory() for _, f in data]
 hrd = pm.host_clouds([(t.data_ptr(), t.shape[0]) for t in host_rd])
 hrf = pm.host_clouds([(t.data_ptr(), t.shape[0]) for t in host_rf])
-for spec in specs[:3]:
+for spec in (specs if os.environ.get('PGS_SWEEP_HOST_ALL') else specs[:3]):
     f = [int(x) for x in spec.split(":")]
     ctx.set_batch_streams(f[0])
     ctx.set_option("batch_chunk", f[1])
