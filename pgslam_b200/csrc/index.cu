@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(256) leaf_box_kernel(const BuildJob* __restric
   float* me = sb[0][threadIdx.x];
   me[0] = lo[0]; me[1] = lo[1]; me[2] = hi[0];
   me[3] = hi[1]; me[4] = lo[2]; me[5] = hi[2];
+  if (leaf == 0) {  // node 0 does not exist (1-based heap): an empty box, so that copies of the array read defined values
+    float* n0 = job.nodes;
+    n0[0] = inf; n0[1] = inf; n0[2] = -inf; n0[3] = -inf; n0[4] = inf; n0[5] = -inf;
+  }
   if (leaf < job.P) {
     float* nd = job.nodes + (size_t)(job.P + leaf) * 6;
 #pragma unroll
