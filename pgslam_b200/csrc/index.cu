@@ -43,18 +43,26 @@ bbox_kernel(const BuildJob* __restrict__ jobs, const float* __restrict__ shift, 
     lo[1] = min(lo[1], uy); hi[1] = max(hi[1], uy);
     lo[2] = min(lo[2], uz); hi[2] = max(hi[2], uz);
   }
+  // one set of atomics per block: the boxes of a batch share a few L2 lines, and atomics on one line are
+  // served one after the other (per warp they were most of this kernel's time)
+  __shared__ unsigned slot[8][6];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
     hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
   }
   if ((threadIdx.x & 31) == 0) {
-    unsigned* bb = bbox + 6 * blockIdx.y;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      atomicMin(bb + d, lo[d]);
-      atomicMax(bb + 3 + d, hi[d]);
-    }
+    for (int d = 0; d < 3; ++d) { slot[threadIdx.x >> 5][d] = lo[d]; slot[threadIdx.x >> 5][3 + d] = hi[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_lo = threadIdx.x < 3;
+    unsigned v = slot[0][threadIdx.x];
+    for (int q = 1; q < 8; ++q) v = is_lo ? min(v, slot[q][threadIdx.x]) : max(v, slot[q][threadIdx.x]);
+    unsigned* bb = bbox + 6 * blockIdx.y;
+    if (is_lo) atomicMin(bb + threadIdx.x, v);
+    else atomicMax(bb + threadIdx.x, v);
   }
 }
 

@@ -49,6 +49,56 @@ __global__ void kd_iota_kernel(const KdCloud* __restrict__ clouds, uint32_t* __r
   if (i < clouds[b].n) vals[(size_t)b * span + i] = (uint32_t)i;
 }
 
+__global__ void kd_box_init_kernel(unsigned* __restrict__ bbox, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bbox[i] = (i % 6 < 3) ? 0xffffffffu : 0u;
+}
+
+// A 256-thread block's (lo, hi) merged into a segment's box {lo.xyz, hi.xyz} of ordered-uint coordinates:
+// one set of atomics per BLOCK.  (Per warp they were the whole run time of these kernels: the boxes of
+// a batch share a few L2 lines, and atomics on one line are served one after the other.)
+// Every thread of the block must call it; `slot` is 8 x 6 words of shared memory.
+__device__ __forceinline__ void kd_box_commit(unsigned* __restrict__ box, unsigned (&lo)[3], unsigned (&hi)[3],
+                                              unsigned (*slot)[6]) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = __reduce_min_sync(0xffffffffu, lo[d]);
+    hi[d] = __reduce_max_sync(0xffffffffu, hi[d]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { slot[w][d] = lo[d]; slot[w][3 + d] = hi[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_lo = threadIdx.x < 3;
+    unsigned v = slot[0][threadIdx.x];
+    for (int q = 1; q < 8; ++q) v = is_lo ? min(v, slot[q][threadIdx.x]) : max(v, slot[q][threadIdx.x]);
+    // an empty block leaves lo = 0xffffffff / hi = 0: both are no-ops on the box
+    if (is_lo) atomicMin(box + threadIdx.x, v);
+    else atomicMax(box + threadIdx.x, v);
+  }
+  __syncthreads();  // the slots may be used again
+}
+
+// the identity order and the cloud's bounding box (the only segment of level 0) in one pass
+__global__ void __launch_bounds__(256)
+kd_iota_box_kernel(const KdCloud* __restrict__ clouds, uint32_t* __restrict__ vals, int span, unsigned* __restrict__ bbox) {
+  __shared__ unsigned slot[8][6];
+  const int b = blockIdx.y;
+  const KdCloud c = clouds[b];
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    vals[(size_t)b * span + i] = (uint32_t)i;
+    const float4 p = c.pts[i];
+    const unsigned u[3] = {f2ord(p.x), f2ord(p.y), f2ord(p.z)};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo[d] = min(lo[d], u[d]); hi[d] = max(hi[d], u[d]); }
+  }
+  kd_box_commit(bbox + 6 * b, lo, hi, slot);
+}
+
 __global__ void kd_jobs_kernel(const KdCloud* __restrict__ clouds, int n_clouds, int segs, int S,
                                int* __restrict__ job_n, unsigned* __restrict__ bbox) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,12 +238,13 @@ kd_hist_kernel(const KdCloud* __restrict__ clouds, const uint32_t* __restrict__ 
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // the last block owns the segment's merged histogram
+  // the last block owns the segment's merged histogram: read it and leave it cleared for the next level
   const int target = S / 2;  // the left child takes the first S/2 slots
   unsigned mine[kSplitBins / 256], sum = 0;
 #pragma unroll
   for (int u = 0; u < kSplitBins / 256; ++u) {
     mine[u] = __ldcg(&gh[tid * (kSplitBins / 256) + u]);
+    gh[tid * (kSplitBins / 256) + u] = 0u;
     sum += mine[u];
   }
   scan[tid] = sum;
@@ -255,9 +306,11 @@ kd_part_count_kernel(const KdCloud* __restrict__ clouds, int segs, int S, const 
 __global__ void __launch_bounds__(256)
 kd_part_scatter_kernel(const KdCloud* __restrict__ clouds, int segs, int S, const uint32_t* __restrict__ vals_in,
                        uint32_t* __restrict__ vals_out, const unsigned short* __restrict__ keys,
-                       const SplitMeta* __restrict__ meta, const int2* __restrict__ counts, int ntiles) {
+                       const SplitMeta* __restrict__ meta, const int2* __restrict__ counts, int ntiles,
+                       unsigned* __restrict__ child_bbox) {
   __shared__ int wl[8], we[8];
   __shared__ int tile_l, tile_e;
+  __shared__ unsigned slot[8][6];
   const int j = blockIdx.y;
   const int cnt = seg_count(clouds[j / segs].n, j % segs, S);
   if (cnt == 0) return;
@@ -304,6 +357,17 @@ kd_part_scatter_kernel(const KdCloud* __restrict__ clouds, int segs, int S, cons
   for (int q = 0; q < w; ++q) { off_l += wl[q]; off_e += we[q]; }
   const int half = S / 2;
   const int off_g = w0 - off_l - off_e;
+  // child_bbox (null at the last global level): the boxes of the next level's segments 2j and 2j+1 are
+  // reduced here, where every point's side is known, instead of in a pass of their own
+  const float4* __restrict__ pts = clouds[j / segs].pts;
+  unsigned llo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, lhi[3] = {0u, 0u, 0u};
+  unsigned rlo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, rhi[3] = {0u, 0u, 0u};
+  float4 pt[8];
+  if (child_bbox) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (side[r] != 3) pt[r] = pts[val[r]];
+  }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     if (side[r] == 3) continue;
@@ -317,6 +381,19 @@ kd_part_scatter_kernel(const KdCloud* __restrict__ clouds, int segs, int S, cons
       dst = half + (mt.n_eq - mt.tie) + off_g + rank[r];
     }
     vals_out[base + dst] = val[r];
+    if (child_bbox) {
+      const unsigned u[3] = {f2ord(pt[r].x), f2ord(pt[r].y), f2ord(pt[r].z)};
+      const bool left = dst < half;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        if (left) { llo[d] = min(llo[d], u[d]); lhi[d] = max(lhi[d], u[d]); }
+        else { rlo[d] = min(rlo[d], u[d]); rhi[d] = max(rhi[d], u[d]); }
+      }
+    }
+  }
+  if (child_bbox) {
+    kd_box_commit(child_bbox + 6 * (size_t)(2 * j), llo, lhi, slot);
+    kd_box_commit(child_bbox + 6 * (size_t)(2 * j + 1), rlo, rhi, slot);
   }
 }
 
@@ -585,29 +662,46 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
   DBuf<uint32_t> keys_a(ctx, total), keys_b(ctx, total), vals_b(ctx, total);
   uint32_t* cur = d_vals_out;   // the buffer that holds the current order
   uint32_t* other = vals_b.p;
-  kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, cur, span);
-  ctx_count_launches(ctx, 1);
   // PGS_KD_SORT_LEVELS=1 brings back the earlier global levels (full segmented radix sorts on
   // 16 / 8-bit keys) for comparison: 2.2 ms per 96 clouds against 1.1 ms for the median split
   static const bool sort_levels = std::getenv("PGS_KD_SORT_LEVELS") && std::atoi(std::getenv("PGS_KD_SORT_LEVELS")) != 0;
   int level = 0;
   int n_levels = 0;
   while ((span >> n_levels) > kLocal) ++n_levels;
-  const int max_jobs = n_levels > 0 ? B << (n_levels - 1) : 0;
-  const int max_tiles = ceil_div(std::min(span, max_n), kSplitTile);
-  DBuf<unsigned> hist;
-  DBuf<unsigned> tickets;
-  DBuf<SplitMeta> meta;
-  DBuf<int2> counts;
   if (!sort_levels && n_levels > 0) {
-    hist.reset(ctx, (size_t)max_jobs * kSplitBins);
-    tickets.reset(ctx, (size_t)max_jobs);
+    // median split: per level histogram -> tile counts -> scatter; the scatter also reduces the boxes of
+    // the two children, the last block of a histogram leaves it cleared (3 launches per level)
+    const int max_jobs = B << (n_levels - 1);
+    const int max_tiles = ceil_div(std::min(span, max_n), kSplitTile);
+    DBuf<unsigned> hist(ctx, (size_t)max_jobs * kSplitBins);
+    hist.zero();
+    DBuf<unsigned> tickets(ctx, (size_t)max_jobs);
     tickets.zero();
-    meta.reset(ctx, (size_t)max_jobs);
-    counts.reset(ctx, (size_t)B * max_tiles * 2 + max_jobs);  // tiles per job halve as jobs double
+    DBuf<SplitMeta> meta(ctx, (size_t)max_jobs);
+    DBuf<int2> counts(ctx, (size_t)B * max_tiles * 2 + max_jobs);  // tiles per job halve as jobs double
+    const int all_boxes = 6 * B * ((1 << n_levels) - 1);          // level l starts at 6 * B * (2^l - 1)
+    DBuf<unsigned> bbox(ctx, (size_t)all_boxes);
+    kd_box_init_kernel<<<ceil_div(all_boxes, 256), 256, 0, st>>>(bbox.p, all_boxes);
+    kd_iota_box_kernel<<<dim3(std::max(1, std::min(ceil_div(max_n, 1024), 128)), B), 256, 0, st>>>(clouds.p, cur, span, bbox.p);
+    ctx_count_launches(ctx, 2);
+    unsigned short* keys16 = reinterpret_cast<unsigned short*>(keys_a.p);
+    for (; level < n_levels; ++level) {
+      const int segs = 1 << level, S = span >> level, jobs = B * segs;
+      const int ntiles = ceil_div(std::min(S, max_n), kSplitTile);
+      unsigned* boxes = bbox.p + (size_t)6 * B * (segs - 1);
+      unsigned* child_boxes = level + 1 < n_levels ? bbox.p + (size_t)6 * B * (2 * segs - 1) : nullptr;
+      const dim3 grid(ntiles, jobs);
+      kd_hist_kernel<<<grid, 256, 0, st>>>(clouds.p, cur, span, segs, S, boxes, keys16, hist.p, tickets.p, meta.p);
+      kd_part_count_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, keys16, meta.p, counts.p, ntiles);
+      kd_part_scatter_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, cur, other, keys16, meta.p, counts.p, ntiles, child_boxes);
+      ctx_count_launches(ctx, 3);
+      std::swap(cur, other);
+    }
+  } else {
+    kd_iota_kernel<<<dim3(ceil_div(max_n, 256), B), 256, 0, st>>>(clouds.p, cur, span);
+    ctx_count_launches(ctx, 1);
   }
-  unsigned short* keys16 = reinterpret_cast<unsigned short*>(keys_a.p);
-  for (; (span >> level) > kLocal; ++level) {
+  for (; level < n_levels; ++level) {  // the sort-based levels (comparison build only)
     const int segs = 1 << level, S = span >> level, jobs = B * segs;
     DBuf<int> job_n(ctx, jobs);
     DBuf<unsigned> bbox(ctx, (size_t)6 * jobs);
@@ -615,22 +709,10 @@ void kd_order_batched(Ctx* ctx, const std::vector<const float4*>& pts, const std
     const int seg_max = std::min(S, max_n);
     kd_bbox_kernel<<<dim3(std::max(1, std::min(ceil_div(seg_max, 2048), 64)), jobs), 256, 0, st>>>(clouds.p, cur, span,
                                                                                                  segs, S, bbox.p);
-    ctx_count_launches(ctx, 2);
-    if (!sort_levels) {
-      const int ntiles = ceil_div(seg_max, kSplitTile);
-      PGS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)jobs * kSplitBins * sizeof(unsigned), st));
-      const dim3 grid(ntiles, jobs);
-      kd_hist_kernel<<<grid, 256, 0, st>>>(clouds.p, cur, span, segs, S, bbox.p, keys16, hist.p, tickets.p, meta.p);
-      kd_part_count_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, keys16, meta.p, counts.p, ntiles);
-      kd_part_scatter_kernel<<<grid, 256, 0, st>>>(clouds.p, segs, S, cur, other, keys16, meta.p, counts.p, ntiles);
-      ctx_count_launches(ctx, 3);
-      std::swap(cur, other);
-      continue;
-    }
     const int key_bits = level < kFineLevels ? 16 : 8;
     kd_key_kernel<<<dim3(ceil_div(seg_max, 256), jobs), 256, 0, st>>>(clouds.p, cur, span, segs, S, bbox.p, keys_a.p,
                                                                       (float)((1 << key_bits) - 1));
-    ctx_count_launches(ctx, 1);
+    ctx_count_launches(ctx, 3);
     // jobs are laid out back to back with stride S: cloud b, segment s starts at (b*segs + s) * S
     const bool in_b = radix_sort_pairs<uint32_t>(ctx, keys_a.p, keys_b.p, cur, other, job_n.p, jobs, S, seg_max, key_bits);
     if (in_b) std::swap(cur, other);  // a one-pass sort leaves the order in the other buffer
