@@ -1173,3 +1173,30 @@ def test_cloud_files_through_the_c_abi(pm, pair30k, tmp_path, ext):
         c = pm.DataPoints.load(str(p3))
         assert c.getNbPoints() == n and np.array_equal(c.features[1], 2 * np.arange(n, dtype=np.float32))
         assert np.array_equal(c.getDescriptorByName("intensity")[0], (np.arange(n) % 250).astype(np.float32))
+
+
+def test_sort_based_kd_levels_give_the_same_neighbours(pm, pair120k):
+    """PGS_KD_SORT_LEVELS=1 (the comparison build of the index: sorted global levels) is read once per
+    process, so it runs in a child: any valid tree must return the same exact neighbours."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    rd, rf, _ = pair120k
+    m = pm.Matcher("KDTreeMatcher", {"knn": 3})
+    m.init(pm.DataPoints(rf))
+    got = m.findClosests(pm.DataPoints(rd[:, :20000]))
+    want = hashlib.sha256(np.ascontiguousarray(got.ids).tobytes() + np.ascontiguousarray(got.dists).tobytes()).hexdigest()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import hashlib, numpy as np\n"
+        "from pgslam_b200 import pm, synth\n"
+        "rd, rf, _ = synth.scan_pair(5, beams=64, az_steps=1875)\n"
+        "m = pm.Matcher('KDTreeMatcher', {'knn': 3})\n"
+        "m.init(pm.DataPoints(rf))\n"
+        "g = m.findClosests(pm.DataPoints(rd[:, :20000]))\n"
+        "print(hashlib.sha256(np.ascontiguousarray(g.ids).tobytes() + np.ascontiguousarray(g.dists).tobytes()).hexdigest())\n")
+    env = dict(os.environ, PGS_KD_SORT_LEVELS="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == want
