@@ -50,35 +50,7 @@ class Acc:
 def scan(q, leaf, acc):
     seg = sp[leaf * L:(leaf + 1) * L]
     for dd in ((seg - q) ** 2).sum(1): acc.offer(float(dd))
-def single(j, group=1):
-    q = sp[j]; acc = Acc(); leaf = j // L
-    first = leaf & ~((1 << group) - 1)
-    for l in range(first, first + (1 << group)):
-        if l < nl: scan(q, l, acc)
-    steps = 0; leaves = 0
-    node = (P + leaf) >> group; d = depth - group
-    while d > 0:
-        sib = node ^ 1
-        steps += 0.5  # sibling test (cheap, batched)
-        if lb(q, sib) <= acc.bound():
-            # traverse_from
-            stack = [sib]
-            while stack:
-                x = stack.pop()
-                if x >= P:
-                    if x - P < nl: scan(q, x - P, acc); leaves += 1
-                    continue
-                steps += 1
-                l0, l1 = lb(q, 2 * x), lb(q, 2 * x + 1)
-                near, far, ln, lf = (2 * x, 2 * x + 1, l0, l1) if l0 <= l1 else (2 * x + 1, 2 * x, l1, l0)
-                if lf <= acc.bound(): stack.append(('f', far))
-                if ln <= acc.bound(): stack.append(near)
-                # emulate re-test of far at pop time
-                stack = [s for s in stack]
-            
-        node >>= 1; d -= 1
-    return steps, leaves
-# simpler faithful emulation: recursion with re-test
+# the per-thread walk: nearest child first, the far child re-tested against the tighter bound
 def trav(q, x, acc, cnt):
     if x >= P:
         if x - P < nl: scan(q, x - P, acc); cnt[1] += 1
