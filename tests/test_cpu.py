@@ -756,3 +756,26 @@ def test_epsilon_is_rejected_not_ignored():
             "print(pm.check_config(util.to_yaml(dict(util.C2, matcher={'KDTreeMatcher': {'knn': 1, 'epsilon': 3.16}}))))" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
     assert int(out.strip()) > 0
+
+
+def test_tools_and_bench_compile():
+    """every script under tools/ (and bench.py, __graft_entry__.py) is at least valid Python"""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"),
+                                                                     os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 10
+    for f in files:
+        with open(f) as fh:
+            ast.parse(fh.read(), filename=f)
+
+
+def test_clock_sampler_without_a_gpu_reports_why():
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    if out["sm_mhz"] is None:
+        assert out["reasons"]
